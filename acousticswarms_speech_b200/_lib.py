@@ -1,0 +1,71 @@
+"""ctypes binding of libasw.so (include/asw.h).  There is no CPU fallback: if the
+library is missing or a call fails, this raises."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libasw.so")
+
+# every symbol include/asw.h declares (tests check the export list against the header)
+SYMBOLS = [
+    "asw_version", "asw_last_error", "asw_launch_count",
+    "asw_srp_create", "asw_srp_destroy", "asw_srp_score",
+    "asw_srp_num_windows", "asw_srp_num_frames",
+    "asw_srp_read_cc", "asw_srp_gcc_layout", "asw_srp_read_gcc",
+    "asw_map_topk", "asw_shift_stack", "asw_shift_stack_norm",
+]
+
+
+class AswError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libasw.so (once).  Raises if it has not been built -- never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AswError(
+            f"{LIB_PATH} is missing: build it with `python -m acousticswarms_speech_b200.build` "
+            "(or __graft_entry__.build()).  This package has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, i32, f32 = c.c_void_p, c.c_int, c.c_float
+    lib.asw_version.restype = i32
+    lib.asw_last_error.restype = c.c_char_p
+    lib.asw_launch_count.restype = c.c_longlong
+    lib.asw_srp_create.argtypes = [c.POINTER(vp), i32, i32, i32, vp, i32, i32, i32, i32, f32, i32]
+    lib.asw_srp_destroy.argtypes = [vp]
+    lib.asw_srp_score.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    lib.asw_srp_num_windows.argtypes = [i32, i32]
+    lib.asw_srp_num_frames.argtypes = [i32, i32, i32]
+    lib.asw_srp_read_cc.argtypes = [vp, vp, vp]
+    lib.asw_srp_gcc_layout.argtypes = [vp, vp, vp, vp, c.POINTER(i32), c.POINTER(i32)]
+    lib.asw_srp_read_gcc.argtypes = [vp, vp, vp]
+    lib.asw_map_topk.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
+    lib.asw_shift_stack.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.asw_shift_stack_norm.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    if hasattr(lib, "asw_peaks_create"):
+        lib.asw_peaks_create.argtypes = [c.POINTER(vp), i32, i32, i32, i32, i32, vp, vp]
+        lib.asw_peaks_destroy.argtypes = [vp]
+        lib.asw_peaks_find.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp]
+    for name in SYMBOLS:
+        fn = getattr(lib, name, None)
+        if fn is not None and name not in ("asw_last_error", "asw_launch_count"):
+            fn.restype = i32
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().asw_last_error().decode("utf-8", "replace")
+        raise AswError(f"libasw error {rc}: {msg}")
+
+
+def launch_count():
+    return int(load().asw_launch_count())

@@ -1,0 +1,448 @@
+// api.cu -- C ABI of libasw.so (declared in include/asw.h): handle management, host-side table
+// construction and the launch sequence of the scoring path.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "common.cuh"
+
+namespace asw {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace asw
+
+using namespace asw;
+
+struct asw_srp {
+    int device = 0, M = 0, P = 0, G = 0, Gpad = 0;
+    int nfft = 0, hop = 0, bin0 = 0, bin1 = 0, F = 0, U = 0;
+    float tol = 0.f;
+    // per-pair lag-table layout (host copies) and device mirrors
+    std::vector<int> lag_lo, n_entries, npad, off;
+    int tab_len = 0;
+    int *d_lag_lo = nullptr, *d_n_entries = nullptr, *d_npad = nullptr, *d_off = nullptr;
+    uint32_t* d_pos = nullptr;   // [P][Gpad] Q12.20
+    float2* d_tw1024 = nullptr;  // [1024]
+    float2* d_twpost = nullptr;  // [F]
+    // staging groups of the gather kernel, one set per window-chunk size
+    std::vector<int> grp_begin;
+    int* d_grp_begin = nullptr;
+    int n_groups = 0, grp_wc = 0, smem_bytes = 0;
+    // workspace (grown on demand)
+    float2* d_cc_part = nullptr;
+    size_t cc_part_cap = 0;
+    float2* d_cc = nullptr;
+    size_t cc_cap = 0;
+    float* d_gcc = nullptr;
+    size_t gcc_cap = 0;
+    // shape of the last score call (for the stage taps)
+    int last_B = 0, last_Nw = 0;
+};
+
+namespace {
+
+int build_groups(asw_srp* h, int wc) {
+    const int budget = srp_gather_smem_budget();
+    h->grp_begin.clear();
+    h->grp_begin.push_back(0);
+    int cur = 0, max_bytes = 0;
+    for (int p = 0; p < h->P; ++p) {
+        const int bytes = wc * h->npad[p] * (int)sizeof(float);
+        if (bytes > budget) {
+            set_error("lag table of pair %d (%d entries x %d windows) exceeds the shared-memory stage of %d bytes; "
+                      "lower the oversampling",
+                      p, h->npad[p], wc, budget);
+            return ASW_ERR_RANGE;
+        }
+        if (cur + bytes > budget) {
+            h->grp_begin.push_back(p);
+            cur = 0;
+        }
+        cur += bytes;
+        if (cur > max_bytes) max_bytes = cur;
+    }
+    h->grp_begin.push_back(h->P);
+    h->n_groups = (int)h->grp_begin.size() - 1;
+    h->grp_wc = wc;
+    h->smem_bytes = max_bytes;
+    if (h->d_grp_begin) cudaFree(h->d_grp_begin);
+    h->d_grp_begin = nullptr;
+    ASW_CUDA_CHECK(cudaMalloc(&h->d_grp_begin, sizeof(int) * h->grp_begin.size()));
+    ASW_CUDA_CHECK(cudaMemcpy(h->d_grp_begin, h->grp_begin.data(), sizeof(int) * h->grp_begin.size(),
+                              cudaMemcpyHostToDevice));
+    return ASW_OK;
+}
+
+template <typename T>
+int ensure(T** ptr, size_t* cap, size_t need) {
+    if (need <= *cap) return ASW_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc(ptr, need * sizeof(T));
+    if (e != cudaSuccess) {
+        set_error("device allocation of %zu bytes failed: %s", need * sizeof(T), cudaGetErrorString(e));
+        return ASW_ERR_ALLOC;
+    }
+    *cap = need;
+    return ASW_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int asw_version(void) { return 100; }
+const char* asw_last_error(void) { return g_err; }
+long long asw_launch_count(void) { return g_launches.load(); }
+
+int asw_srp_num_windows(int T, int win_len) {
+    if (win_len < 2) return 0;
+    const int step = win_len / 2;
+    int n = 0;
+    for (int j = 0; j < T / step - 1; ++j) {
+        if (j * step + win_len > T) break;
+        ++n;
+    }
+    return n;
+}
+
+int asw_srp_num_frames(int win_len, int nfft, int hop) {
+    if (win_len < nfft || hop <= 0) return 0;
+    return (win_len - nfft) / hop + 1;
+}
+
+int asw_srp_create(asw_srp_t** out, int device, int M, int G, const double* lag, int nfft, int hop, int bin0, int bin1,
+                   float tol, int oversample) {
+    if (!out || !lag) {
+        set_error("asw_srp_create: null argument");
+        return ASW_ERR_ARG;
+    }
+    *out = nullptr;
+    if (M < 2 || M > kMaxMics || G < 1) {
+        set_error("asw_srp_create: M=%d (2..%d) / G=%d unsupported", M, kMaxMics, G);
+        return ASW_ERR_ARG;
+    }
+    if (nfft != kNfft || hop != kHop) {
+        set_error("asw_srp_create: only nfft=%d, hop=%d is implemented (got %d, %d)", kNfft, kHop, nfft, hop);
+        return ASW_ERR_ARG;
+    }
+    if (bin0 < 0 || bin1 <= bin0 || bin1 > kNfft / 2 || bin1 - bin0 > 256) {
+        set_error("asw_srp_create: bin range [%d, %d) unsupported", bin0, bin1);
+        return ASW_ERR_ARG;
+    }
+    const int U = oversample == 0 ? 4 : oversample;
+    if (U != 1 && U != 2 && U != 4 && U != 8) {
+        set_error("asw_srp_create: oversample must be 1, 2, 4 or 8");
+        return ASW_ERR_ARG;
+    }
+    ASW_CUDA_CHECK(cudaSetDevice(device));
+
+    asw_srp* h = new asw_srp();
+    h->device = device;
+    h->M = M;
+    h->P = M * (M - 1) / 2;
+    h->G = G;
+    h->Gpad = ((G + 2047) / 2048) * 2048;
+    h->nfft = nfft;
+    h->hop = hop;
+    h->bin0 = bin0;
+    h->bin1 = bin1;
+    h->F = bin1 - bin0;
+    h->U = U;
+    h->tol = tol;
+    const int P = h->P;
+
+    // per-pair lag range -> table layout
+    h->lag_lo.resize(P);
+    h->n_entries.resize(P);
+    h->npad.resize(P);
+    h->off.resize(P);
+    int off = 0;
+    for (int p = 0; p < P; ++p) {
+        double mn = lag[p], mx = lag[p];
+        for (int g = 1; g < G; ++g) {
+            const double v = lag[(size_t)g * P + p];
+            if (v < mn) mn = v;
+            if (v > mx) mx = v;
+        }
+        if (!(mn == mn) || !(mx == mx) || fabs(mn) > 1e6 || fabs(mx) > 1e6) {
+            set_error("asw_srp_create: non-finite or absurd lag for pair %d", p);
+            delete h;
+            return ASW_ERR_ARG;
+        }
+        const int lo = (int)floor(mn) - 2, hi = (int)ceil(mx) + 2;
+        const int n = (hi - lo) * U + 1;
+        if (n > kMaxEntries - 4) {
+            set_error("asw_srp_create: pair %d spans %d lag-table entries (limit %d); lower the oversampling", p, n,
+                      kMaxEntries - 4);
+            delete h;
+            return ASW_ERR_RANGE;
+        }
+        h->lag_lo[p] = lo;
+        h->n_entries[p] = n;
+        h->npad[p] = (n + 3) & ~3;
+        h->off[p] = off;
+        off += h->npad[p];
+    }
+    h->tab_len = off;
+
+    // fixed-point positions, transposed to [P][Gpad]; padding rows point at a valid interior entry
+    std::vector<uint32_t> pos((size_t)P * h->Gpad, 2u << kFracBits);
+    const double one = (double)(1u << kFracBits);
+    for (int g = 0; g < G; ++g)
+        for (int p = 0; p < P; ++p) {
+            const double x = (lag[(size_t)g * P + p] - (double)h->lag_lo[p]) * (double)U;
+            double q = floor(x * one + 0.5);
+            const double qmax = (double)(h->n_entries[p] - 3) * one;  // keep i0 + 2 inside the table
+            if (q < one) q = one;
+            if (q > qmax) q = qmax;
+            pos[(size_t)p * h->Gpad + g] = (uint32_t)q;
+        }
+
+    std::vector<float2> tw(kNc), twp(h->F);
+    for (int t = 0; t < kNc; ++t) {
+        const double a = -2.0 * M_PI * (double)t / (double)kNc;
+        tw[t] = make_float2((float)cos(a), (float)sin(a));
+    }
+    for (int f = 0; f < h->F; ++f) {
+        const double a = -2.0 * M_PI * (double)(bin0 + f) / (double)kNfft;
+        twp[f] = make_float2((float)cos(a), (float)sin(a));
+    }
+
+    int rc = ASW_OK;
+    do {
+#define TRY(expr)                                                                          \
+    {                                                                                      \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                     \
+            rc = ASW_ERR_CUDA;                                                             \
+            break;                                                                         \
+        }                                                                                  \
+    }
+        TRY(cudaMalloc(&h->d_lag_lo, sizeof(int) * P));
+        TRY(cudaMalloc(&h->d_n_entries, sizeof(int) * P));
+        TRY(cudaMalloc(&h->d_npad, sizeof(int) * P));
+        TRY(cudaMalloc(&h->d_off, sizeof(int) * P));
+        TRY(cudaMalloc(&h->d_pos, sizeof(uint32_t) * pos.size()));
+        TRY(cudaMalloc(&h->d_tw1024, sizeof(float2) * kNc));
+        TRY(cudaMalloc(&h->d_twpost, sizeof(float2) * h->F));
+        TRY(cudaMemcpy(h->d_lag_lo, h->lag_lo.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+        TRY(cudaMemcpy(h->d_n_entries, h->n_entries.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+        TRY(cudaMemcpy(h->d_npad, h->npad.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+        TRY(cudaMemcpy(h->d_off, h->off.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+        TRY(cudaMemcpy(h->d_pos, pos.data(), sizeof(uint32_t) * pos.size(), cudaMemcpyHostToDevice));
+        TRY(cudaMemcpy(h->d_tw1024, tw.data(), sizeof(float2) * kNc, cudaMemcpyHostToDevice));
+        TRY(cudaMemcpy(h->d_twpost, twp.data(), sizeof(float2) * h->F, cudaMemcpyHostToDevice));
+#undef TRY
+    } while (0);
+    if (rc != ASW_OK) {
+        asw_srp_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return ASW_OK;
+}
+
+int asw_srp_destroy(asw_srp_t* h) {
+    if (!h) return ASW_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_lag_lo);
+    cudaFree(h->d_n_entries);
+    cudaFree(h->d_npad);
+    cudaFree(h->d_off);
+    cudaFree(h->d_pos);
+    cudaFree(h->d_tw1024);
+    cudaFree(h->d_twpost);
+    cudaFree(h->d_grp_begin);
+    cudaFree(h->d_cc_part);
+    cudaFree(h->d_cc);
+    cudaFree(h->d_gcc);
+    delete h;
+    return ASW_OK;
+}
+
+int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len, float* map_dev, void* stream) {
+    if (!h || !mix_dev || !map_dev || B < 1) {
+        set_error("asw_srp_score: null handle/buffer or B < 1");
+        return ASW_ERR_ARG;
+    }
+    if (B > 65535) {
+        set_error("asw_srp_score: B=%d exceeds the grid limit 65535; split the batch", B);
+        return ASW_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int Nw = asw_srp_num_windows(T, win_len);
+    const int Nf = asw_srp_num_frames(win_len, h->nfft, h->hop);
+    if (Nw < 1 || Nf < 1) {
+        // no analysis window fits: the reference leaves the map at its zero initialisation (:253)
+        ASW_CUDA_CHECK(cudaMemsetAsync(map_dev, 0, sizeof(float) * (size_t)B * h->G, s));
+        h->last_B = B;
+        h->last_Nw = 0;
+        return ASW_OK;
+    }
+    // frame groups: enough CTAs for ~2 waves when the batch is small, whole windows when it is large
+    int NG = 1;
+    {
+        const long long base = (long long)B * Nw;
+        const long long want = 2LL * kNumSms * 4;  // several CTAs per SM are resident
+        if (base < want) NG = (int)((want + base - 1) / base);
+        if (NG > Nf) NG = Nf;
+        if (NG < 1) NG = 1;
+    }
+    int FG = (Nf + NG - 1) / NG;
+    NG = (Nf + FG - 1) / FG;
+
+    const int wc = Nw < srp_gather_windows_per_chunk() ? Nw : srp_gather_windows_per_chunk();
+    if (h->grp_wc != wc) {
+        int rc = build_groups(h, wc);
+        if (rc != ASW_OK) return rc;
+    }
+    int rc;
+    if ((rc = ensure(&h->d_cc_part, &h->cc_part_cap, (size_t)B * Nw * NG * h->F * h->P)) != ASW_OK) return rc;
+    if ((rc = ensure(&h->d_cc, &h->cc_cap, (size_t)B * Nw * h->F * h->P)) != ASW_OK) return rc;
+    if ((rc = ensure(&h->d_gcc, &h->gcc_cap, (size_t)B * Nw * h->tab_len)) != ASW_OK) return rc;
+
+    StftCcParams sp{};
+    sp.mix = mix_dev;
+    sp.cc_part = h->d_cc_part;
+    sp.tw1024 = h->d_tw1024;
+    sp.twpost = h->d_twpost;
+    sp.B = B;
+    sp.M = h->M;
+    sp.T = T;
+    sp.Nw = Nw;
+    sp.step = win_len / 2;
+    sp.Nf = Nf;
+    sp.NG = NG;
+    sp.FG = FG;
+    sp.bin0 = h->bin0;
+    sp.F = h->F;
+    sp.P = h->P;
+    sp.tol = h->tol;
+    if ((rc = launch_stft_cc(sp, s)) != ASW_OK) return rc;
+
+    GccParams gp{};
+    gp.cc_part = h->d_cc_part;
+    gp.gcc = h->d_gcc;
+    gp.cc_out = h->d_cc;
+    gp.lag_lo = h->d_lag_lo;
+    gp.n_entries = h->d_n_entries;
+    gp.npad = h->d_npad;
+    gp.off = h->d_off;
+    gp.B = B;
+    gp.Nw = Nw;
+    gp.NG = NG;
+    gp.F = h->F;
+    gp.P = h->P;
+    gp.bin0 = h->bin0;
+    gp.U = h->U;
+    gp.tab_len = h->tab_len;
+    gp.inv_nf = 1.0f / (float)Nf;
+    gp.scale = (float)(1.0 / ((double)h->F * (double)h->P));
+    if ((rc = launch_gcc(gp, s)) != ASW_OK) return rc;
+
+    SrpGatherParams rp{};
+    rp.gcc = h->d_gcc;
+    rp.pos = h->d_pos;
+    rp.npad = h->d_npad;
+    rp.off = h->d_off;
+    rp.grp_begin = h->d_grp_begin;
+    rp.map = map_dev;
+    rp.B = B;
+    rp.G = h->G;
+    rp.Gpad = h->Gpad;
+    rp.P = h->P;
+    rp.Nw = Nw;
+    rp.tab_len = h->tab_len;
+    rp.n_groups = h->n_groups;
+    rp.smem_bytes = h->smem_bytes;
+    if ((rc = launch_srp_gather(rp, s)) != ASW_OK) return rc;
+
+    h->last_B = B;
+    h->last_Nw = Nw;
+    return ASW_OK;
+}
+
+int asw_srp_read_cc(asw_srp_t* h, float* cc_dev, void* stream) {
+    if (!h || !cc_dev) {
+        set_error("asw_srp_read_cc: null argument");
+        return ASW_ERR_ARG;
+    }
+    const size_t n = (size_t)h->last_B * h->last_Nw * h->F * h->P;
+    if (n == 0) return ASW_OK;
+    ASW_CUDA_CHECK(cudaMemcpyAsync(cc_dev, h->d_cc, n * sizeof(float2), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return ASW_OK;
+}
+
+int asw_srp_gcc_layout(asw_srp_t* h, int* lag_lo, int* n_entries, int* offset, int* table_len, int* oversample) {
+    if (!h) {
+        set_error("asw_srp_gcc_layout: null handle");
+        return ASW_ERR_ARG;
+    }
+    for (int p = 0; p < h->P; ++p) {
+        if (lag_lo) lag_lo[p] = h->lag_lo[p];
+        if (n_entries) n_entries[p] = h->n_entries[p];
+        if (offset) offset[p] = h->off[p];
+    }
+    if (table_len) *table_len = h->tab_len;
+    if (oversample) *oversample = h->U;
+    return ASW_OK;
+}
+
+int asw_srp_read_gcc(asw_srp_t* h, float* gcc_dev, void* stream) {
+    if (!h || !gcc_dev) {
+        set_error("asw_srp_read_gcc: null argument");
+        return ASW_ERR_ARG;
+    }
+    const size_t n = (size_t)h->last_B * h->last_Nw * h->tab_len;
+    if (n == 0) return ASW_OK;
+    ASW_CUDA_CHECK(cudaMemcpyAsync(gcc_dev, h->d_gcc, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return ASW_OK;
+}
+
+int asw_map_topk(const float* map_dev, int B, int G, int K, int idx_offset, float* val_dev, int32_t* idx_dev,
+                 void* stream) {
+    if (!map_dev || !val_dev || !idx_dev || B < 1 || G < 0) {
+        set_error("asw_map_topk: null buffer or bad shape");
+        return ASW_ERR_ARG;
+    }
+    return launch_topk(map_dev, B, G, K, idx_offset, val_dev, idx_dev, (cudaStream_t)stream);
+}
+
+int asw_shift_stack(const float* mix_dev, const int32_t* shifts_dev, const int32_t* mix_index_dev, int N, int B, int M,
+                    int T, float* out_dev, void* stream) {
+    if (!mix_dev || !shifts_dev || !out_dev || N < 0 || B < 1 || M < 1 || M > kMaxMics || T < 1) {
+        set_error("asw_shift_stack: null buffer or bad shape (N=%d B=%d M=%d T=%d)", N, B, M, T);
+        return ASW_ERR_ARG;
+    }
+    return launch_shift_stack(mix_dev, shifts_dev, mix_index_dev, N, B, M, T, out_dev, (cudaStream_t)stream);
+}
+
+int asw_shift_stack_norm(const float* mix_dev, const int32_t* shifts_dev, const int32_t* mix_index_dev, int N, int B,
+                         int M, int T, float* out_dev, float* means_dev, float* stds_dev, double* work_dev,
+                         void* stream) {
+    if (!mix_dev || !shifts_dev || !out_dev || !means_dev || !stds_dev || !work_dev || N < 0 || B < 1 || M < 1 ||
+        M > kMaxMics || T < 2) {
+        set_error("asw_shift_stack_norm: null buffer or bad shape (N=%d B=%d M=%d T=%d)", N, B, M, T);
+        return ASW_ERR_ARG;
+    }
+    return launch_shift_stack_norm(mix_dev, shifts_dev, mix_index_dev, N, B, M, T, out_dev, means_dev, stds_dev,
+                                   work_dev, (cudaStream_t)stream);
+}
+
+}  // extern "C"

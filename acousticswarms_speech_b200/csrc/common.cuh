@@ -1,0 +1,93 @@
+// common.cuh -- shared helpers for libasw (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/asw.h"
+
+namespace asw {
+
+constexpr int kNfft = 2048;          // STFT frame (sep/helpers/constants.py:27)
+constexpr int kNc = kNfft / 2;       // complex FFT length after even/odd packing
+constexpr int kHop = kNfft / 4;      // SRP_Prunning.py:406
+constexpr int kMaxMics = 32;
+constexpr int kFracBits = 20;        // lag position fixed point: Q12.20
+constexpr int kMaxEntries = 1 << (32 - kFracBits);
+constexpr int kNumSms = 148;         // B200
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define ASW_CUDA_CHECK(expr)                                                        \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) {                                                    \
+            asw::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                           __FILE__, __LINE__);                                     \
+            return ASW_ERR_CUDA;                                                    \
+        }                                                                           \
+    } while (0)
+
+#define ASW_LAUNCH_CHECK(name)                                                      \
+    do {                                                                            \
+        cudaError_t _e = cudaGetLastError();                                        \
+        if (_e != cudaSuccess) {                                                    \
+            asw::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+            return ASW_ERR_CUDA;                                                    \
+        }                                                                           \
+        asw::count_launch();                                                        \
+    } while (0)
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// ---- kernel launchers (defined in the .cu files) ---------------------------------------------
+
+struct StftCcParams {
+    const float* mix;      // [B][M][T]
+    float2* cc_part;       // [B][Nw][NG][F][P]
+    const float2* tw1024;  // [1024]  exp(-2 pi i t / 1024)
+    const float2* twpost;  // [F]     exp(-2 pi i k / 2048), k = bin0 + f
+    int B, M, T, Nw, step, Nf, NG, FG, bin0, F, P;
+    float tol;
+};
+int launch_stft_cc(const StftCcParams& p, cudaStream_t s);
+
+struct GccParams {
+    const float2* cc_part;  // [B][Nw][NG][F][P]
+    float* gcc;             // [B][tab_len * Nw]  pair-major: pair p at Nw*off[p], then [Nw][npad[p]]
+    float2* cc_out;         // optional [B][Nw][F][P] summed + 1/Nf scaled (parity tap), may be null
+    const int* lag_lo;      // [P] first lag (integer samples) of pair p's table
+    const int* n_entries;   // [P] valid entries
+    const int* npad;        // [P] entries padded to a multiple of 4
+    const int* off;         // [P] float offset of the pair segment (per window unit)
+    int B, Nw, NG, F, P, bin0, U, tab_len;
+    float inv_nf, scale;    // 1/Nf ; 1/(F*P)
+};
+int launch_gcc(const GccParams& p, cudaStream_t s);
+
+struct SrpGatherParams {
+    const float* gcc;       // as above
+    const uint32_t* pos;    // [P][Gpad] Q12.20 position inside the pair's table
+    const int* npad;        // [P]
+    const int* off;         // [P]
+    const int* grp_begin;   // [n_groups + 1] pair ranges staged together
+    float* map;             // [B][G]
+    int B, G, Gpad, P, Nw, tab_len, n_groups, smem_bytes;
+};
+int launch_srp_gather(const SrpGatherParams& p, cudaStream_t s);
+int srp_gather_windows_per_chunk();
+int srp_gather_smem_budget();
+
+int launch_topk(const float* map, int B, int G, int K, int idx_offset, float* val, int32_t* idx, cudaStream_t s);
+
+int launch_shift_stack(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int B, int M,
+                       int T, float* out, cudaStream_t s);
+int launch_shift_stack_norm(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int B,
+                            int M, int T, float* out, float* means, float* stds, double* work, cudaStream_t s);
+
+}  // namespace asw

@@ -1,0 +1,229 @@
+// shift_stack.cu -- per-hypercube circular channel shift, stacked into the separator's input layout.
+//
+// Reference: the loop of DataParallelSpotModel.shift_and_sep (sep/training/JointModel/network.py:75-83)
+// with roll_by_gather (:12-25):  data[n] = gather(mix, 1, (t - shifts) mod T), shifts = -round([0,*off]),
+// i.e.   out[n][c][t] = mix[c][(t + r[n][c]) mod T].
+// The reference builds an int64 (M, T) index tensor per patch and calls torch.gather; here one
+// launch writes the whole (N, M, T) batch.  The kernel is HBM-write bound: 4*N*M*T bytes out, the
+// (M, T) source stays L2-resident.  Each thread produces 16 B per store from two aligned 16 B loads
+// (the source is misaligned by r mod 4) and only the one vector per row that straddles the wrap
+// point takes the scalar path.
+//
+// The fused variant also applies normalize_input (sep/training/SpeakerLocalization/network.py:28-40):
+// x = round(x * 2^15) / 2^15; ref = mean over mics; (x - mean_t(ref)) / std_t(ref) (unbiased).
+#include "common.cuh"
+
+namespace asw {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kVpt = 4;  // 16-byte vectors per thread
+
+__device__ __forceinline__ int pymod(int a, int n) {
+    int r = a % n;
+    return r < 0 ? r + n : r;
+}
+
+__device__ __forceinline__ float quant16(float x) { return rintf(x * 32768.f) * (1.f / 32768.f); }
+
+// Load 4 consecutive source samples starting at circular position s (0 <= s < T), T % 4 == 0.
+__device__ __forceinline__ float4 load4_circ(const float* __restrict__ src, int s, int T) {
+    if (s + 3 < T) {
+        const int base = s & ~3;
+        const int o = s & 3;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src + base));
+        if (o == 0) return a;
+        const int nb = (base + 4 < T) ? base + 4 : 0;
+        const float4 c = __ldg(reinterpret_cast<const float4*>(src + nb));
+        if (o == 1) return make_float4(a.y, a.z, a.w, c.x);
+        if (o == 2) return make_float4(a.z, a.w, c.x, c.y);
+        return make_float4(a.w, c.x, c.y, c.z);
+    }
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int q = s + i;
+        if (q >= T) q -= T;
+        v[i] = __ldg(src + q);
+    }
+    return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+template <bool NORM>
+__global__ void __launch_bounds__(kThreads) shift_stack_vec_kernel(const float* __restrict__ mix,
+                                                                    const int32_t* __restrict__ shifts,
+                                                                    const int32_t* __restrict__ mix_index, int M, int T,
+                                                                    float* __restrict__ out,
+                                                                    const double* __restrict__ work,
+                                                                    float* __restrict__ means, float* __restrict__ stds) {
+    const int row = blockIdx.x;  // n * M + c
+    const int n = row / M, c = row - n * M;
+    const int mi = mix_index ? mix_index[n] : 0;
+    const float* src = mix + ((size_t)mi * M + c) * (size_t)T;
+    float4* dst = reinterpret_cast<float4*>(out + (size_t)row * T);
+    const int r = pymod(shifts[row], T);
+    const int T4 = T >> 2;
+    float mean = 0.f, inv_std = 1.f;
+    if (NORM) {
+        const double S = work[2 * n], SS = work[2 * n + 1];
+        const double mu = S / (double)T;
+        const double var = (SS - S * mu) / (double)(T - 1);
+        const float sd = (float)sqrt(var > 0.0 ? var : 0.0);
+        mean = (float)mu;
+        inv_std = sd;  // divide below, like the reference
+        if (c == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+            means[n] = mean;
+            stds[n] = sd;
+        }
+    }
+    const int v0 = blockIdx.y * (kThreads * kVpt) + threadIdx.x;
+    float4 val[kVpt];
+#pragma unroll
+    for (int v = 0; v < kVpt; ++v) {
+        const int t4 = v0 + v * kThreads;
+        if (t4 < T4) {
+            int s = 4 * t4 + r;
+            if (s >= T) s -= T;
+            val[v] = load4_circ(src, s, T);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < kVpt; ++v) {
+        const int t4 = v0 + v * kThreads;
+        if (t4 < T4) {
+            float4 x = val[v];
+            if (NORM) {
+                x.x = (quant16(x.x) - mean) / inv_std;
+                x.y = (quant16(x.y) - mean) / inv_std;
+                x.z = (quant16(x.z) - mean) / inv_std;
+                x.w = (quant16(x.w) - mean) / inv_std;
+            }
+            __stcs(dst + t4, x);
+        }
+    }
+}
+
+// Generic fallback for T % 4 != 0 or unaligned buffers.
+template <bool NORM>
+__global__ void __launch_bounds__(kThreads) shift_stack_scalar_kernel(const float* __restrict__ mix,
+                                                                       const int32_t* __restrict__ shifts,
+                                                                       const int32_t* __restrict__ mix_index, int M,
+                                                                       int T, float* __restrict__ out,
+                                                                       const double* __restrict__ work,
+                                                                       float* __restrict__ means,
+                                                                       float* __restrict__ stds) {
+    const int row = blockIdx.x;
+    const int n = row / M, c = row - n * M;
+    const int mi = mix_index ? mix_index[n] : 0;
+    const float* src = mix + ((size_t)mi * M + c) * (size_t)T;
+    float* dst = out + (size_t)row * T;
+    const int r = pymod(shifts[row], T);
+    float mean = 0.f, sd = 1.f;
+    if (NORM) {
+        const double S = work[2 * n], SS = work[2 * n + 1];
+        const double mu = S / (double)T;
+        const double var = (SS - S * mu) / (double)(T - 1);
+        sd = (float)sqrt(var > 0.0 ? var : 0.0);
+        mean = (float)mu;
+        if (c == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+            means[n] = mean;
+            stds[n] = sd;
+        }
+    }
+    for (int t = blockIdx.y * (kThreads * kVpt * 4) + threadIdx.x, e = min(T, (int)(blockIdx.y + 1) * (kThreads * kVpt * 4));
+         t < e; t += kThreads) {
+        int s = t + r;
+        if (s >= T) s -= T;
+        float x = __ldg(src + s);
+        if (NORM) x = (quant16(x) - mean) / sd;
+        dst[t] = x;
+    }
+}
+
+// Pass 1 of the fused variant: per patch, sum and sum of squares over t of the mic-averaged,
+// re-quantised, shifted signal (accumulated in double, one atomic pair per CTA).
+__global__ void __launch_bounds__(kThreads) shift_ref_stats_kernel(const float* __restrict__ mix,
+                                                                    const int32_t* __restrict__ shifts,
+                                                                    const int32_t* __restrict__ mix_index, int M, int T,
+                                                                    double* __restrict__ work) {
+    __shared__ int s_r[kMaxMics];
+    __shared__ double s_red[2][kThreads / 32];
+    const int n = blockIdx.x;
+    const int mi = mix_index ? mix_index[n] : 0;
+    const float* src = mix + (size_t)mi * M * (size_t)T;
+    if (threadIdx.x < M) s_r[threadIdx.x] = pymod(shifts[n * M + threadIdx.x], T);
+    __syncthreads();
+    const float inv_m = 1.f / (float)M;
+    double sum = 0.0, sq = 0.0;
+    const int t_end = min(T, (int)(blockIdx.y + 1) * (kThreads * 16));
+    for (int t = blockIdx.y * (kThreads * 16) + threadIdx.x; t < t_end; t += kThreads) {
+        float ref = 0.f;
+        for (int c = 0; c < M; ++c) {
+            int s = t + s_r[c];
+            if (s >= T) s -= T;
+            ref += quant16(__ldg(src + (size_t)c * T + s));
+        }
+        ref *= inv_m;
+        sum += (double)ref;
+        sq += (double)ref * (double)ref;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        sum += __shfl_down_sync(0xffffffffu, sum, d);
+        sq += __shfl_down_sync(0xffffffffu, sq, d);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        s_red[0][warp] = sum;
+        s_red[1][warp] = sq;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int i = 0; i < kThreads / 32; ++i) {
+            a += s_red[0][i];
+            c += s_red[1][i];
+        }
+        atomicAdd(work + 2 * n, a);
+        atomicAdd(work + 2 * n + 1, c);
+    }
+}
+
+template <bool NORM>
+int launch_rows(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int M, int T, float* out,
+                const double* work, float* means, float* stds, cudaStream_t s) {
+    const bool vec = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(mix) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const int per_cta = kThreads * kVpt * 4;  // samples per CTA
+    dim3 grid((unsigned)(N * M), (unsigned)((T + per_cta - 1) / per_cta));
+    if (vec) {
+        shift_stack_vec_kernel<NORM><<<grid, kThreads, 0, s>>>(mix, shifts, mix_index, M, T, out, work, means, stds);
+        ASW_LAUNCH_CHECK("shift_stack_vec_kernel");
+    } else {
+        shift_stack_scalar_kernel<NORM><<<grid, kThreads, 0, s>>>(mix, shifts, mix_index, M, T, out, work, means, stds);
+        ASW_LAUNCH_CHECK("shift_stack_scalar_kernel");
+    }
+    return ASW_OK;
+}
+
+}  // namespace
+
+int launch_shift_stack(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int B, int M, int T,
+                       float* out, cudaStream_t s) {
+    (void)B;
+    if (N == 0) return ASW_OK;
+    return launch_rows<false>(mix, shifts, mix_index, N, M, T, out, nullptr, nullptr, nullptr, s);
+}
+
+int launch_shift_stack_norm(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int B, int M,
+                            int T, float* out, float* means, float* stds, double* work, cudaStream_t s) {
+    (void)B;
+    if (N == 0) return ASW_OK;
+    ASW_CUDA_CHECK(cudaMemsetAsync(work, 0, sizeof(double) * 2 * (size_t)N, s));
+    dim3 grid((unsigned)N, (unsigned)((T + kThreads * 16 - 1) / (kThreads * 16)));
+    shift_ref_stats_kernel<<<grid, kThreads, 0, s>>>(mix, shifts, mix_index, M, T, work);
+    ASW_LAUNCH_CHECK("shift_ref_stats_kernel");
+    return launch_rows<true>(mix, shifts, mix_index, N, M, T, out, work, means, stds, s);
+}
+
+}  // namespace asw

@@ -1,0 +1,134 @@
+// srp_gather.cu -- steered response power of every hypercube by gathering the pair GCC tables at
+// the hypercube's fractional pair lags, summed over pairs, max over analysis windows.
+//
+// Reference arithmetic (sep/Traditional_SP/SRP_Prunning.py):
+//   :428-429  map_w[g] = sum_{f,p} Re(CC[f,p] tab[g,f,p]) / F / P    == sum_p R_p(tau[g,p])  (see gcc.cu)
+//   :253,:430 SRP_map = maximum(SRP_map, map_w), SRP_map starts at zeros  (so the map is >= 0)
+//
+// Staging is pair-major: a group of pairs x up to kWc windows of GCC table is copied to shared
+// memory, each thread then takes its hypercubes' fixed-point lag positions for those pairs (one
+// coalesced load, reused by every window and computed once into 4-tap Lagrange weights), and
+// gathers 4 adjacent table entries per (hypercube, pair, window).  The per-window sums stay in
+// registers; the max over windows is taken at the end.  The kernel is shared-memory-bandwidth
+// bound (16 B per gather).
+#include "common.cuh"
+
+namespace asw {
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kWc = 8;                    // windows per staging chunk
+constexpr int kSmemBudget = 200 * 1024;   // bytes of GCC table staged at once
+
+template <int GPT>
+__global__ void __launch_bounds__(kThreads, 1) srp_gather_kernel(SrpGatherParams p) {
+    extern __shared__ __align__(16) float s_tab[];
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const int g_base = blockIdx.x * (kThreads * GPT);
+    const float* gcc_b = p.gcc + (size_t)b * p.tab_len * p.Nw;
+
+    float best[GPT];
+#pragma unroll
+    for (int gi = 0; gi < GPT; ++gi) best[gi] = 0.f;
+
+    for (int w0 = 0; w0 < p.Nw; w0 += kWc) {
+        const int wc = min(kWc, p.Nw - w0);
+        float acc[kWc][GPT];
+#pragma unroll
+        for (int w = 0; w < kWc; ++w)
+#pragma unroll
+            for (int gi = 0; gi < GPT; ++gi) acc[w][gi] = 0.f;
+
+        for (int grp = 0; grp < p.n_groups; ++grp) {
+            const int p0 = p.grp_begin[grp], p1 = p.grp_begin[grp + 1];
+            __syncthreads();  // everyone is done reading the previous stage
+            int sm_off = 0;
+            for (int pp = p0; pp < p1; ++pp) {
+                const int npd = p.npad[pp];
+                const float4* src =
+                    reinterpret_cast<const float4*>(gcc_b + (size_t)p.Nw * p.off[pp] + (size_t)w0 * npd);
+                float4* dst = reinterpret_cast<float4*>(s_tab + sm_off);
+                const int n4 = (wc * npd) >> 2;
+                for (int i = tid; i < n4; i += kThreads) dst[i] = __ldg(src + i);
+                sm_off += wc * npd;
+            }
+            __syncthreads();
+            sm_off = 0;
+            for (int pp = p0; pp < p1; ++pp) {
+                const int npd = p.npad[pp];
+#pragma unroll
+                for (int gi = 0; gi < GPT; ++gi) {
+                    const uint32_t q = __ldg(p.pos + (size_t)pp * p.Gpad + g_base + gi * kThreads + tid);
+                    const int i0 = (int)(q >> kFracBits);
+                    const float f = (float)(q & ((1u << kFracBits) - 1)) * (1.0f / (float)(1 << kFracBits));
+                    // 4-tap Lagrange weights for nodes -1, 0, 1, 2
+                    const float fm1 = f - 1.f, fm2 = f - 2.f, fp1 = f + 1.f;
+                    const float c0 = -(1.f / 6.f) * f * fm1 * fm2;
+                    const float c1 = 0.5f * fp1 * fm1 * fm2;
+                    const float c2 = -0.5f * fp1 * f * fm2;
+                    const float c3 = (1.f / 6.f) * fp1 * f * fm1;
+                    const float* t = s_tab + sm_off + i0 - 1;
+#pragma unroll
+                    for (int w = 0; w < kWc; ++w) {
+                        if (w < wc) {
+                            float v = c0 * t[0];
+                            v = fmaf(c1, t[1], v);
+                            v = fmaf(c2, t[2], v);
+                            v = fmaf(c3, t[3], v);
+                            acc[w][gi] += v;
+                            t += npd;
+                        }
+                    }
+                }
+                sm_off += wc * npd;
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < kWc; ++w)
+            if (w < wc) {
+#pragma unroll
+                for (int gi = 0; gi < GPT; ++gi) best[gi] = fmaxf(best[gi], acc[w][gi]);
+            }
+    }
+#pragma unroll
+    for (int gi = 0; gi < GPT; ++gi) {
+        const int g = g_base + gi * kThreads + tid;
+        if (g < p.G) p.map[(size_t)b * p.G + g] = best[gi];
+    }
+}
+
+template <int GPT>
+int launch_t(const SrpGatherParams& p, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(srp_gather_kernel<GPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            kSmemBudget));
+        attr_set = true;
+    }
+    const int tile = kThreads * GPT;
+    dim3 grid((p.G + tile - 1) / tile, p.B);
+    srp_gather_kernel<GPT><<<grid, kThreads, p.smem_bytes, s>>>(p);
+    ASW_LAUNCH_CHECK("srp_gather_kernel");
+    return ASW_OK;
+}
+
+}  // namespace
+
+int srp_gather_windows_per_chunk() { return kWc; }
+int srp_gather_smem_budget() { return kSmemBudget; }
+
+int launch_srp_gather(const SrpGatherParams& p, cudaStream_t s) {
+    if (p.smem_bytes > kSmemBudget) {
+        set_error("srp_gather: stage of %d bytes exceeds the shared-memory budget", p.smem_bytes);
+        return ASW_ERR_RANGE;
+    }
+    // Larger tiles amortise the table staging; smaller tiles fill the 148 SMs when the batch is small.
+    const long long tiles4 = (long long)((p.G + kThreads * 4 - 1) / (kThreads * 4)) * p.B;
+    if (tiles4 >= 2 * kNumSms) return launch_t<4>(p, s);
+    const long long tiles2 = (long long)((p.G + kThreads * 2 - 1) / (kThreads * 2)) * p.B;
+    if (tiles2 >= kNumSms) return launch_t<2>(p, s);
+    return launch_t<1>(p, s);
+}
+
+}  // namespace asw

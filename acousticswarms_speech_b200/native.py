@@ -1,0 +1,192 @@
+"""Thin torch-facing wrappers over the C ABI (include/asw.h).
+
+torch is used for device memory and streams only; every computation below is a
+libasw.so kernel.  All tensors handed to the library must live on the handle's
+CUDA device; anything else raises (no CPU fallback)."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .constants import HOP, PHAT_TOL, n_fft
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(t, name, dtype):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.AswError(f"{name} must be a CUDA tensor (this path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.AswError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.AswError(f"{name} must be contiguous")
+
+
+def pair_list(M):
+    return [(i, j) for i in range(M) for j in range(i + 1, M)]
+
+
+def pair_lags(grids, mic_pos, fs, C):
+    """Fractional pair lags in samples, (G, P) float64: the phase slope of the reference's steering
+    table (sep/Traditional_SP/SRP_Prunning.py:368-381, :228).  Mic height is ignored (:375)."""
+    grids = np.asarray(grids, dtype=np.float64)
+    mic_pos = np.asarray(mic_pos, dtype=np.float64)
+    d = np.sqrt((grids[None, :, 0] - mic_pos[:, None, 0]) ** 2 + (grids[None, :, 1] - mic_pos[:, None, 1]) ** 2
+                + grids[None, :, 2] ** 2)
+    prs = pair_list(mic_pos.shape[0])
+    return np.ascontiguousarray(np.stack([fs * (d[i] - d[j]) / C for (i, j) in prs], axis=1))
+
+
+class NativeSRP:
+    """Device-resident scoring handle (asw_srp_t) for one geometry."""
+
+    def __init__(self, lag_samples, num_mic, device=None, bin0=2, bin1=200, tol=PHAT_TOL, oversample=0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.AswError("no CUDA device: the SRP-PHAT path is CUDA-only (sm_100a), there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        lag = np.ascontiguousarray(lag_samples, dtype=np.float64)
+        self.M = int(num_mic)
+        self.P = self.M * (self.M - 1) // 2
+        if lag.ndim != 2 or lag.shape[1] != self.P:
+            raise _lib.AswError(f"lag_samples must be (G, {self.P})")
+        self.G = lag.shape[0]
+        self.F = bin1 - bin0
+        self._h = ctypes.c_void_p()
+        _lib.check(self.lib.asw_srp_create(ctypes.byref(self._h), self.device.index or 0, self.M, self.G,
+                                           lag.ctypes.data_as(ctypes.c_void_p), n_fft, HOP, bin0, bin1,
+                                           ctypes.c_float(tol), oversample))
+        self._last = (0, 0)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.asw_srp_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def num_windows(self, T, win_len):
+        return int(self.lib.asw_srp_num_windows(T, win_len))
+
+    def score(self, mix, win_len, out=None):
+        """mix (B, M, T) or (M, T) float32 CUDA -> map (B, G) float32 CUDA."""
+        if mix.dim() == 2:
+            mix = mix.unsqueeze(0)
+        _require_cuda(mix, "mix", torch.float32)
+        B, M, T = mix.shape
+        if M != self.M:
+            raise _lib.AswError(f"mix has {M} channels, handle was built for {self.M}")
+        if out is None:
+            out = torch.empty((B, self.G), device=mix.device, dtype=torch.float32)
+        else:
+            _require_cuda(out, "out", torch.float32)
+        _lib.check(self.lib.asw_srp_score(self._h, _ptr(mix), B, T, int(win_len), _ptr(out), _stream(mix.device)))
+        self._last = (B, self.num_windows(T, win_len))
+        return out
+
+    def read_cc(self):
+        """CC_flat of the last score call: (B, Nw, F, P) complex64."""
+        B, Nw = self._last
+        buf = torch.empty((B, Nw, self.F, self.P, 2), device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.asw_srp_read_cc(self._h, _ptr(buf), _stream(self.device)))
+        return torch.view_as_complex(buf)
+
+    def gcc_layout(self):
+        lo = (ctypes.c_int * self.P)()
+        n = (ctypes.c_int * self.P)()
+        off = (ctypes.c_int * self.P)()
+        tl, U = ctypes.c_int(), ctypes.c_int()
+        _lib.check(self.lib.asw_srp_gcc_layout(self._h, lo, n, off, ctypes.byref(tl), ctypes.byref(U)))
+        return np.array(lo), np.array(n), np.array(off), tl.value, U.value
+
+    def read_gcc(self):
+        """GCC lag tables of the last score call: flat (B, Nw * table_len) float32 (pair-major)."""
+        B, Nw = self._last
+        _, _, _, tl, _ = self.gcc_layout()
+        buf = torch.empty((B, Nw * tl), device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.asw_srp_read_gcc(self._h, _ptr(buf), _stream(self.device)))
+        return buf
+
+
+def map_topk(srp_map, K, idx_offset=0):
+    """(B, G) float32 CUDA -> values (B, K) float32, indices (B, K) int32 (descending, ties to lower index)."""
+    if srp_map.dim() == 1:
+        srp_map = srp_map.unsqueeze(0)
+    _require_cuda(srp_map, "srp_map", torch.float32)
+    B, G = srp_map.shape
+    val = torch.empty((B, K), device=srp_map.device, dtype=torch.float32)
+    idx = torch.empty((B, K), device=srp_map.device, dtype=torch.int32)
+    _lib.check(_lib.load().asw_map_topk(_ptr(srp_map), B, G, int(K), int(idx_offset), _ptr(val), _ptr(idx),
+                                        _stream(srp_map.device)))
+    return val, idx
+
+
+def shift_stack(mix, shifts, mix_index=None, out=None):
+    """out[n, c, t] = mix[mix_index[n], c, (t + shifts[n, c]) mod T]  (network.py:12-25, 75-83).
+
+    mix (B, M, T) or (M, T) float32 CUDA; shifts (N, M) int32 CUDA; mix_index (N,) int32 CUDA or None."""
+    if mix.dim() == 2:
+        mix = mix.unsqueeze(0)
+    _require_cuda(mix, "mix", torch.float32)
+    _require_cuda(shifts, "shifts", torch.int32)
+    B, M, T = mix.shape
+    N = shifts.shape[0]
+    if shifts.shape != (N, M):
+        raise _lib.AswError(f"shifts must be (N, {M})")
+    if mix_index is not None:
+        _require_cuda(mix_index, "mix_index", torch.int32)
+    if out is None:
+        out = torch.empty((N, M, T), device=mix.device, dtype=torch.float32)
+    else:
+        _require_cuda(out, "out", torch.float32)
+        if out.numel() < N * M * T:
+            raise _lib.AswError("out is too small")
+    if N == 0:
+        return out
+    _lib.check(_lib.load().asw_shift_stack(_ptr(mix), _ptr(shifts), _ptr(mix_index) if mix_index is not None else None,
+                                           N, B, M, T, _ptr(out), _stream(mix.device)))
+    return out
+
+
+def shift_stack_norm(mix, shifts, mix_index=None, out=None):
+    """shift_stack fused with normalize_input (SpeakerLocalization/network.py:28-40).
+    Returns (data_norm (N, M, T), means (N, 1, 1), stds (N, 1, 1))."""
+    if mix.dim() == 2:
+        mix = mix.unsqueeze(0)
+    _require_cuda(mix, "mix", torch.float32)
+    _require_cuda(shifts, "shifts", torch.int32)
+    B, M, T = mix.shape
+    N = shifts.shape[0]
+    if mix_index is not None:
+        _require_cuda(mix_index, "mix_index", torch.int32)
+    if out is None:
+        out = torch.empty((N, M, T), device=mix.device, dtype=torch.float32)
+    means = torch.empty((N,), device=mix.device, dtype=torch.float32)
+    stds = torch.empty((N,), device=mix.device, dtype=torch.float32)
+    work = torch.empty((N, 2), device=mix.device, dtype=torch.float64)
+    _lib.check(_lib.load().asw_shift_stack_norm(_ptr(mix), _ptr(shifts),
+                                                _ptr(mix_index) if mix_index is not None else None, N, B, M, T,
+                                                _ptr(out), _ptr(means), _ptr(stds), _ptr(work),
+                                                _stream(mix.device)))
+    return out, means.view(N, 1, 1), stds.view(N, 1, 1)
+
+
+def offsets_to_shifts(offsets):
+    """Patch.sample_offset list -> (N, M) int32 read offsets: r[0] = 0, r[c] = round_half_even(float32(off[c-1]))
+    (sep/training/JointModel/network.py:81-82)."""
+    off = np.asarray(offsets)
+    if off.ndim == 1:
+        off = off[None]
+    v = np.concatenate([np.zeros((off.shape[0], 1)), off], axis=1).astype(np.float32)
+    return np.rint(v).astype(np.int32)

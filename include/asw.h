@@ -1,0 +1,133 @@
+/*
+ * asw.h -- C ABI of libasw.so: B200-native (sm_100a) SRP-PHAT scoring of TDoA
+ * hypercubes + per-hypercube circular shift-and-stack.
+ *
+ * The reference (uw-x/AcousticSwarms-Speech) is 100 % Python and has no FFI of
+ * its own; these entry points are what a binding for its hot path would call.
+ * Each one cites the reference interface it replaces (paths relative to the
+ * reference root).  INTEGRATION.md shows the ctypes stubs a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative asw_status code; the
+ *     message of the last failure on the calling thread is asw_last_error().
+ *   - all *_dev pointers are device pointers on the handle's device, contiguous,
+ *     owned by the caller (e.g. torch tensors' data_ptr()).  The handle owns only
+ *     its tables and workspace.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Calls are stream-ordered and do not synchronise unless stated.
+ *   - no CPU fallback, no dispatch: without a CUDA device every call fails with
+ *     ASW_ERR_CUDA.
+ *   - a handle is not thread-safe (the reference is single-threaded per
+ *     Mic_Array); use one handle per device / per host thread.
+ */
+#ifndef ASW_H_
+#define ASW_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum asw_status {
+    ASW_OK = 0,
+    ASW_ERR_ARG = -1,      /* bad argument (null pointer, unsupported size)   */
+    ASW_ERR_CUDA = -2,     /* CUDA runtime error (message has the details)    */
+    ASW_ERR_ALLOC = -3,    /* device allocation failed                         */
+    ASW_ERR_RANGE = -4     /* geometry exceeds a kernel limit (see message)    */
+} asw_status;
+
+typedef struct asw_srp asw_srp_t;
+
+/* Library / build info. asw_version() = major*10000 + minor*100 + patch. */
+int asw_version(void);
+const char* asw_last_error(void);
+/* Number of CUDA kernels this library has launched in the calling process
+ * (bench.py reports it as gpu_launches). */
+long long asw_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * SRP-PHAT scoring handle.
+ *
+ * Replaces the per-geometry state of SRP_PHAT.__init__ that the scoring loop
+ * uses: the (G, F, P) float64 steering table `mode_mat_flat_real/imag`
+ * (sep/Traditional_SP/SRP_Prunning.py:221-243, generate_mod_vector :368-381).
+ * Instead of the table the handle keeps, per hypercube g and mic pair p
+ * (i<j, row-major), the fractional pair lag in samples
+ *     lag[g*P + p] = fs * (dist(g, mic_i) - dist(g, mic_j)) / C
+ * with dist as in :375 (mic height ignored).  The host computes it in fp64
+ * from the reference's own `grids` / `mic_pos`.
+ *
+ *   M          microphones (2..32); P = M(M-1)/2
+ *   G          hypercubes (Grid_clusters)
+ *   nfft, hop  STFT frame / hop; only nfft = 2048 is implemented (constants.py:27),
+ *              hop = nfft/4 (SRP_Prunning.py:406)
+ *   bin0,bin1  scored bins [bin0, bin1) (constants.py:24-26: 2, 200)
+ *   tol        PHAT magnitude floor (SRP_Prunning.py:384: 1e-8)
+ *   oversample lag-table oversampling U in {1,2,4,8}; 0 selects the default (4)
+ */
+int asw_srp_create(asw_srp_t** out, int device, int M, int G, const double* lag_samples,
+                   int nfft, int hop, int bin0, int bin1, float tol, int oversample);
+int asw_srp_destroy(asw_srp_t* h);
+
+/* SRP_PHAT.SRP_Map_WINDOW_new / SRP_Map_WINDOW_torch
+ * (sep/Traditional_SP/SRP_Prunning.py:384-433) for a batch of B mixtures that
+ * share the geometry: analysis-window framing (:393-403), rectangular-window
+ * STFT (:404-409), per-channel PHAT (:414-416), pair cross-spectra averaged over
+ * frames (:418-426), steered response at every hypercube (:428-429), max over
+ * windows starting from zero (:253, :430).
+ *   mix_dev  [B][M][T] float32           map_dev  [B][G] float32 (output)
+ *   win_len  analysis-window length (sep/Mic_Array.py:160-163: 36000 | 24000)
+ * Windows: step = win_len/2, j < T/step - 1, j*step + win_len <= T. */
+int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len,
+                  float* map_dev, void* stream);
+
+/* Number of analysis windows / STFT frames the call above uses (host-side helper;
+ * mirrors SRP_Prunning.py:393-403 and the pyroomacoustics frame rule). */
+int asw_srp_num_windows(int T, int win_len);
+int asw_srp_num_frames(int win_len, int nfft, int hop);
+
+/* Stage taps for parity tests: results of the most recent asw_srp_score call.
+ *   cc_dev   [B][Nw][F][P][2] float32 -- CC_flat (:426), real/imag interleaved
+ *   gcc_dev  [B][P-segments...]       -- band-limited GCC lag tables (layout via
+ *            asw_srp_gcc_layout), already scaled by 1/(F*P) */
+int asw_srp_read_cc(asw_srp_t* h, float* cc_dev, void* stream);
+int asw_srp_gcc_layout(asw_srp_t* h, int* lag_lo /*P*/, int* n_entries /*P*/, int* offset /*P*/,
+                       int* table_len, int* oversample);
+int asw_srp_read_gcc(asw_srp_t* h, float* gcc_dev, void* stream);
+
+/* MAX_POWER (:432) and the K best hypercubes per mixture, descending by value,
+ * ties broken by lower index.  Used for the multi-GPU merge and as the
+ * pruning pre-filter; K in {1..1024}.
+ *   val_dev [B][K] float32, idx_dev [B][K] int32 (index into [0,G) + idx_offset);
+ *   entries beyond G are (-inf, -1). */
+int asw_map_topk(const float* map_dev, int B, int G, int K, int idx_offset,
+                 float* val_dev, int32_t* idx_dev, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Shift-and-stack: the loop of DataParallelSpotModel.shift_and_sep
+ * (sep/training/JointModel/network.py:75-83) with roll_by_gather (:12-25):
+ *     out[n][c][t] = mix[mix_index[n]][c][(t + shifts[n][c]) mod T]
+ * where shifts[n][0] = 0 and shifts[n][c] = round_half_even(float32(
+ * patch.sample_offset[c-1])) (:81-82); any int32 value is accepted (reduced
+ * mod T with Python semantics).
+ *   mix_dev    [B][M][T] float32
+ *   shifts_dev [N][M] int32
+ *   mix_index_dev [N] int32 or NULL (all patches read mixture 0)
+ *   out_dev    [N][M][T] float32 -- the network's input layout (batch, mic, time) */
+int asw_shift_stack(const float* mix_dev, const int32_t* shifts_dev, const int32_t* mix_index_dev,
+                    int N, int B, int M, int T, float* out_dev, void* stream);
+
+/* Same, fused with normalize_input
+ * (sep/training/SpeakerLocalization/network.py:28-40): 16-bit re-quantisation,
+ * mean / unbiased std of the mic-average, (x - mean) / std.
+ *   means_dev, stds_dev [N] float32 (outputs, needed by unnormalize_input :42-47)
+ *   work_dev  [N][2] float64 scratch owned by the caller */
+int asw_shift_stack_norm(const float* mix_dev, const int32_t* shifts_dev, const int32_t* mix_index_dev,
+                         int N, int B, int M, int T, float* out_dev, float* means_dev, float* stds_dev,
+                         double* work_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASW_H_ */

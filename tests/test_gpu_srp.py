@@ -1,0 +1,140 @@
+"""GPU parity: SRP-PHAT scoring stages vs the oracle restatement of
+SRP_PHAT.SRP_Map_WINDOW_torch (sep/Traditional_SP/SRP_Prunning.py:387-433).
+Floating point: 1e-4 relative in fp32 (north_star), measured normwise."""
+import numpy as np
+import pytest
+import torch
+
+from acousticswarms_speech_b200 import synth
+from acousticswarms_speech_b200.constants import freq_bins, n_fft
+from oracle import geometry_oracle, srp_oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def small():
+    scene = synth.small_scene(n_mics=4, seed=2)
+    geo = geometry_oracle.GeometryOracle(scene.mic_positions, scene.roi, build_fine=False)
+    return scene, geo
+
+
+def _native(scene, grids, **kw):
+    from acousticswarms_speech_b200 import native
+    lag = native.pair_lags(grids, scene.mic_positions, scene.fs, 343.0)
+    return native.NativeSRP(lag, scene.mic_positions.shape[0], **kw)
+
+
+@pytest.mark.parametrize("T", [48000, 96000])
+def test_stage_parity_small(cuda_device, small, T):
+    scene, geo = small
+    mix = synth.mixture(scene, 2, T, seed=7)
+    srp = _native(scene, geo.grids)
+    win = srp_oracle.window_length(T)
+    got = srp.score(torch.from_numpy(mix).cuda(), win)
+    torch.cuda.synchronize()
+    want, st = srp_oracle.score(mix, geo.grids, scene.mic_positions, freq_bins, scene.fs, n_fft, stages=True)
+    # cross-spectra (:418-426)
+    cc = srp.read_cc().cpu().numpy()[0]
+    ref_cc = np.stack(st["CC"])
+    assert cc.shape == ref_cc.shape
+    assert np.abs(cc - ref_cc).max() <= TOL * np.abs(ref_cc).max()
+    # GCC lag tables against a direct float64 evaluation of the same band-limited transform
+    lo, n, off, tl, U = srp.gcc_layout()
+    gcc = srp.read_gcc().cpu().numpy()[0]
+    Nw = ref_cc.shape[0]
+    F, P = ref_cc.shape[1:]
+    worst = 0.0
+    scale = 0.0
+    for p in range(P):
+        lags = lo[p] + np.arange(n[p]) / U
+        ph = np.exp(2j * np.pi * np.outer(lags, freq_bins) / n_fft)
+        npad = (n[p] + 3) // 4 * 4
+        for w in range(Nw):
+            ref = (ph @ ref_cc[w, :, p].astype(np.complex128)).real / (F * P)
+            seg = gcc[Nw * off[p] + w * npad: Nw * off[p] + w * npad + n[p]]
+            worst = max(worst, np.abs(seg - ref).max())
+            scale = max(scale, np.abs(ref).max())
+    assert worst <= TOL * scale * P      # P pair terms add into one map value
+    # the map (:428-430)
+    g = got.cpu().numpy()[0]
+    assert np.abs(g - want).max() <= TOL * want.max()
+    assert (g >= 0).all()
+
+
+def test_batch_matches_single(cuda_device, small):
+    scene, geo = small
+    T = 72000
+    mixes = synth.mixtures(scene, 2, T, seeds=[1, 2, 3])
+    srp = _native(scene, geo.grids)
+    win = srp_oracle.window_length(T)
+    both = srp.score(torch.from_numpy(mixes).cuda(), win).cpu().numpy()
+    for b in range(3):
+        one = srp.score(torch.from_numpy(mixes[b]).cuda(), win).cpu().numpy()[0]
+        assert np.array_equal(one, both[b])        # deterministic: no atomics on the scoring path
+        want = srp_oracle.score(mixes[b], geo.grids, scene.mic_positions, freq_bins, scene.fs, n_fft)
+        assert np.abs(both[b] - want).max() <= TOL * want.max()
+
+
+def test_short_signal_gives_zero_map(cuda_device, small):
+    scene, geo = small
+    srp = _native(scene, geo.grids)
+    mix = synth.mixture(scene, 1, 30000, seed=1)       # T//step - 1 == 1 but one 24000 window fits
+    got = srp.score(torch.from_numpy(mix).cuda(), 24000).cpu().numpy()[0]
+    want = srp_oracle.score(mix, geo.grids, scene.mic_positions, freq_bins, scene.fs, n_fft, window=24000)
+    assert np.abs(got - want).max() <= TOL * max(want.max(), 1e-12)
+    mix = mix[:, :20000]                               # no window fits: map stays zero (:253)
+    got = srp.score(torch.from_numpy(mix).cuda(), 24000).cpu().numpy()[0]
+    assert (got == 0).all()
+
+
+def test_silence_and_phat_floor(cuda_device, small):
+    scene, geo = small
+    srp = _native(scene, geo.grids)
+    mix = np.zeros((4, 48000), dtype=np.float32)       # |X| < tol everywhere -> pX = 0 -> map = 0
+    got = srp.score(torch.from_numpy(mix).cuda(), 24000).cpu().numpy()[0]
+    assert (got == 0).all()
+
+
+@pytest.mark.parametrize("U", [2, 8])
+def test_oversampling_variants(cuda_device, small, U):
+    scene, geo = small
+    T = 48000
+    mix = synth.mixture(scene, 2, T, seed=9)
+    srp = _native(scene, geo.grids, oversample=U)
+    got = srp.score(torch.from_numpy(mix).cuda(), 24000).cpu().numpy()[0]
+    want = srp_oracle.score(mix, geo.grids, scene.mic_positions, freq_bins, scene.fs, n_fft)
+    assert np.abs(got - want).max() <= TOL * want.max()
+
+
+def test_generic_mic_count(cuda_device):
+    """M > 8 takes the generic cross-spectrum path and multi-group table staging."""
+    rng = np.random.default_rng(4)
+    scene = synth.table_array(10, rng)
+    scene.roi = [2.0, 2.6, 3.2, 3.8, 0.0, 0.4]
+    geo = geometry_oracle.GeometryOracle(scene.mic_positions, scene.roi, build_fine=False)
+    mix = synth.mixture(scene, 2, 48000, seed=3)
+    srp = _native(scene, geo.grids)
+    got = srp.score(torch.from_numpy(mix).cuda(), 24000).cpu().numpy()[0]
+    want = srp_oracle.score(mix, geo.grids, scene.mic_positions, freq_bins, scene.fs, n_fft)
+    assert np.abs(got - want).max() <= TOL * want.max()
+
+
+def test_topk(cuda_device):
+    from acousticswarms_speech_b200 import native
+    rng = np.random.default_rng(0)
+    B, G = 5, 20315
+    m = rng.random((B, G)).astype(np.float32)
+    m[m < 0.27] = 0.0                      # ~27 % exact zeros like a real map
+    m[0, 100] = m[0, 7] = m[0].max()       # exact ties -> lower index first
+    for K in (1, 30, 128, 1000):
+        val, idx = native.map_topk(torch.from_numpy(m).cuda(), K, idx_offset=1000)
+        val, idx = val.cpu().numpy(), idx.cpu().numpy() - 1000
+        for b in range(B):
+            order = np.lexsort((np.arange(G), -m[b]))[:K]
+            assert np.array_equal(idx[b], order)
+            assert np.array_equal(val[b], m[b][order])
+    # K > G pads with (-inf, -1)
+    val, idx = native.map_topk(torch.from_numpy(m[:, :10].copy()).cuda(), 16)
+    assert (idx.cpu().numpy()[:, 10:] == -1).all() and np.isneginf(val.cpu().numpy()[:, 10:]).all()
