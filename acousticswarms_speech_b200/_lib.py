@@ -13,6 +13,7 @@ SYMBOLS = [
     "asw_srp_num_windows", "asw_srp_num_frames",
     "asw_srp_read_cc", "asw_srp_gcc_layout", "asw_srp_read_gcc",
     "asw_map_topk", "asw_shift_stack", "asw_shift_stack_norm",
+    "asw_geometry_cluster",
 ]
 
 
@@ -49,6 +50,7 @@ def load():
     lib.asw_map_topk.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
     lib.asw_shift_stack.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
     lib.asw_shift_stack_norm.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.asw_geometry_cluster.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     if hasattr(lib, "asw_peaks_create"):
         lib.asw_peaks_create.argtypes = [c.POINTER(vp), i32, i32, i32, i32, i32, vp, vp]
         lib.asw_peaks_destroy.argtypes = [vp]

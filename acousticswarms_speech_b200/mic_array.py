@@ -1,0 +1,170 @@
+"""``Mic_Array``: host orchestration of localisation-by-separation's front end.
+
+Mirror of the reference's sep/Mic_Array.py for the three drop-in methods of the hot path --
+``Apply_SRP_PHAT`` (:152-194), ``Spotform_Big_Patch`` (:196-222) and
+``Spotform_Small_Patch_Parallel`` (:225-395) -- with the same signatures, return values and
+per-instance state (``SRP_node``, ``Relative_Threshold``, counters).  Scoring and shift-stack run in
+libasw.so (CUDA); the reference's debug monitor / plotting is dropped.
+"""
+import numpy as np
+import torch
+
+from .constants import (FS, INIT_WIDTH, SPEED_OF_SOUND, SPOT_POWER_THRESHOLD2, SRP_THRESHOLDS,
+                        USE_RELATIVE_SPOT_POWER, freq_bins, n_fft, window_length)
+from .local_utils import binary_search_baseline, max_avg_power, search_area, si_sdr
+from .patch import Patch
+from .srp_phat import SRP_PHAT
+
+
+def weight_mean_pos(patch_list, powers, id_lists):
+    """Power-weighted mean position / offsets of a cluster of fine patches (Mic_Array.py:32-47)."""
+    total_pos = np.zeros((3,))
+    total_power = 0
+    max_power = powers[id_lists[0]]
+    total_offsets = np.zeros(patch_list[0].sample_offset.shape)
+    for _id in id_lists:
+        if powers[_id] < max_power * 0.75:
+            continue
+        total_pos += powers[_id] * patch_list[_id].center_pos()
+        total_offsets += powers[_id] * patch_list[_id].sample_offset
+        total_power += powers[_id]
+    return total_pos / total_power, total_offsets / total_power
+
+
+def find_merge_center(merged_offests, init_area, mic_positions, Big_patch_center):
+    """Mic_Array.py:50-81 (the widening loop only ever tries factor 0, as in the reference)."""
+    num_pair = mic_positions.shape[0] - 1
+    patch_center = Patch(merged_offests, [3 for _ in range(num_pair)], None)
+    area = patch_center.hyperbola_general_area(init_area[0, :], init_area[1, :], init_area[2, :], mic_positions,
+                                               SPEED_OF_SOUND, FS) == 1
+    if np.sum(area) == 0:
+        patch_center.width_list = [3 for _ in range(num_pair)]
+        area = patch_center.hyperbola_general_area(init_area[0, :], init_area[1, :], init_area[2, :],
+                                                   mic_positions, SPEED_OF_SOUND, FS) == 1
+        if np.sum(area) > 0:
+            patch_center.area_points = init_area[:, area]
+        else:
+            patch_center.peak_pos = Big_patch_center
+    else:
+        patch_center.area_points = init_area[:, area]
+    return patch_center
+
+
+class Mic_Array(object):
+    def __init__(self, mic_positions, demo=False, Spk_Range=None, grid_size=0.05, Prone_method="SRP",
+                 MIN_TRIGGER_POWER=0.5, SRP_fast=False, cached=False, cached_folder=None, fs=FS, device=None):
+        if Prone_method != "SRP":
+            raise NotImplementedError("only the default SRP pruner is on the accelerated path "
+                                      "(MUSIC/TOPS are out of scope, sep/Mic_Array.py:167-170)")
+        self.Prone_method = Prone_method
+        self.MIN_TRIGGER_POWER = MIN_TRIGGER_POWER
+        self.visual_save = False
+        self.Range_spk = Spk_Range
+        self.fs = fs
+        self.mic_positions = np.asarray(mic_positions, dtype=np.float64)
+        self.num_mic = self.mic_positions.shape[0]
+        self.upper_bound_pairwise = np.zeros((self.num_mic - 1,))
+        for i in range(1, self.num_mic):
+            self.upper_bound_pairwise[i - 1] = (np.linalg.norm(self.mic_positions[i] - self.mic_positions[0])
+                                                + 0.08) / SPEED_OF_SOUND * fs
+        # SRP_fast selected the torch device in the reference (:123-130); here the path is CUDA-only
+        self.SRP_node = SRP_PHAT(mic_pos=self.mic_positions, freq_bins=freq_bins, Range_spk=Spk_Range,
+                                 grid_size=grid_size, FS=fs, n_fft=n_fft, threshold=list(SRP_THRESHOLDS),
+                                 WIDTH=INIT_WIDTH, device=device, cached=cached, cached_name=cached_folder)
+        self.original_times = 0
+        self.spotforming_times = 0
+
+    def Apply_SRP_PHAT(self, mix_data):
+        """(M, T) float32 tensor -> (patch_list, simple_pos)   (Mic_Array.py:152-194)."""
+        self.SRP_node.reset()
+        self.spotforming_times = 0
+        self.original_times = 0
+        WIN_SIZE = window_length(mix_data.shape[1])
+        self.SRP_node.SRP_Map_WINDOW_new(mix_data, window=WIN_SIZE)
+        patch_list = self.SRP_node.local_source_adaptive()
+        return patch_list, np.zeros((3, 3))
+
+    def Spotform_Big_Patch(self, mix_data, patch_list, spot_model):
+        """Mic_Array.py:196-222."""
+        self.big_spotforming_times = len(patch_list)
+        candidate_finished, powers_with_dis, Relative_Threshold = binary_search_baseline(
+            mix_data, spot_model, patch_list, self.mic_positions)
+        self.Relative_Threshold = Relative_Threshold
+        return candidate_finished
+
+    def small_patch_list(self, candidate_finished):
+        """The patch-list assembly of Spotform_Small_Patch_Parallel (:244-262): fine hypercubes from
+        ``search_area`` plus one width-2 centre patch per candidate."""
+        width_list0 = [2 for _ in range(self.num_mic - 1)]
+        total_patch, patches_indexes, init_area_total, centre_total = [], [0], [], []
+        self.spotforming_times = 0
+        for cand in candidate_finished:
+            patch_processed = search_area([cand], self.mic_positions, self.upper_bound_pairwise)
+            init_area_total.append(cand.area_points)
+            patch_center0 = Patch(cand.sample_offset, width_list0, None, cand.peak_pos)
+            centre = patch_center0.center_pos()
+            centre_total.append(centre)
+            if centre is not None:
+                patch_processed.append(patch_center0)
+            self.spotforming_times += len(patch_processed)
+            total_patch.extend(patch_processed)
+            patches_indexes.append(self.spotforming_times)
+        return total_patch, patches_indexes, init_area_total, centre_total
+
+    def Spotform_Small_Patch_Parallel(self, mix_data, candidate_finished, spot_model, sample_gt=None,
+                                      run_demo_folder=None):
+        """Mic_Array.py:225-395 -> list of (patch_center, audio, power, tag, offsets, big_label)."""
+        output_pair = []
+        if USE_RELATIVE_SPOT_POWER:
+            thr_new = min([SPOT_POWER_THRESHOLD2, self.Relative_Threshold])
+        else:
+            thr_new = SPOT_POWER_THRESHOLD2
+        total_patch, patches_indexes, init_area_total, centre_total = self.small_patch_list(candidate_finished)
+        sep_data_total = spot_model.shift_and_sep(mix_data, total_patch, Strict=1)
+
+        for i in range(len(patches_indexes) - 1):
+            big_offset = candidate_finished[i].sample_offset
+            big_label = -1
+            if sample_gt is not None:
+                for k in range(sample_gt.shape[1]):
+                    if np.amax(np.abs(big_offset - sample_gt[:, k])) < 3.5:
+                        big_label = k
+                        break
+            sep_data = sep_data_total[patches_indexes[i]:patches_indexes[i + 1]]
+            patch_processed = total_patch[patches_indexes[i]:patches_indexes[i + 1]]
+            init_area = init_area_total[i]
+            Big_patch_center = centre_total[i]
+            powers, powers2 = [], []
+            for j in range(len(patch_processed)):
+                sep_data[j, :] = sep_data[j, :] - np.mean(sep_data[j, :])
+                powers.append(np.sum(sep_data[j, :] ** 2))
+                powers2.append(max_avg_power(sep_data[j, :])[0])
+            cpos = candidate_finished[i].center_pos()
+            d = np.linalg.norm(cpos - self.mic_positions[0]) if cpos.shape[0] == 3 else 4
+            if np.amax(powers2) < thr_new / (1 + d):
+                continue
+            sort_idx = np.argsort(-1 * np.array(powers))
+            SI_SDR_THRESHOLD = -4
+            clusters = {}
+            MIN_TRIGGER_POWER2 = self.MIN_TRIGGER_POWER / (3 * 48000) * sep_data.shape[1]
+            for _id in sort_idx:
+                unique = True
+                d = np.linalg.norm(patch_processed[_id].center_pos() - self.mic_positions[0])
+                if powers2[_id] < thr_new / (1 + d) or powers[_id] < MIN_TRIGGER_POWER2:
+                    continue
+                for cluster_id in clusters:
+                    final_candidate_id = clusters[cluster_id][0]
+                    if si_sdr(sep_data[_id, :], sep_data[final_candidate_id]) > SI_SDR_THRESHOLD:
+                        clusters[final_candidate_id].append(_id)
+                        unique = False
+                        break
+                if unique:
+                    clusters[_id] = [_id]
+            for cluster_id in clusters:
+                position, offests = weight_mean_pos(patch_processed, powers, clusters[cluster_id])
+                patch_center = find_merge_center(offests, init_area, self.mic_positions, Big_patch_center)
+                save_offsets = {"audio_offset": patch_processed[cluster_id].sample_offset,
+                                "localization_offset": offests}
+                output_pair.append((patch_center, sep_data[cluster_id, :], powers[cluster_id],
+                                    str(i) + "_" + str(cluster_id), save_offsets, big_label))
+        return output_pair

@@ -153,10 +153,10 @@ def shift_stack(mix, shifts, mix_index=None, out=None):
         if out.numel() < N * M * T:
             raise _lib.AswError("out is too small")
     if N == 0:
-        return out
+        return out[:0]
     _lib.check(_lib.load().asw_shift_stack(_ptr(mix), _ptr(shifts), _ptr(mix_index) if mix_index is not None else None,
                                            N, B, M, T, _ptr(out), _stream(mix.device)))
-    return out
+    return out[:N]
 
 
 def shift_stack_norm(mix, shifts, mix_index=None, out=None):
@@ -172,14 +172,20 @@ def shift_stack_norm(mix, shifts, mix_index=None, out=None):
         _require_cuda(mix_index, "mix_index", torch.int32)
     if out is None:
         out = torch.empty((N, M, T), device=mix.device, dtype=torch.float32)
+    else:
+        _require_cuda(out, "out", torch.float32)
+        if out.numel() < N * M * T:
+            raise _lib.AswError("out is too small")
     means = torch.empty((N,), device=mix.device, dtype=torch.float32)
     stds = torch.empty((N,), device=mix.device, dtype=torch.float32)
     work = torch.empty((N, 2), device=mix.device, dtype=torch.float64)
+    if N == 0:
+        return out[:0], means.view(0, 1, 1), stds.view(0, 1, 1)
     _lib.check(_lib.load().asw_shift_stack_norm(_ptr(mix), _ptr(shifts),
                                                 _ptr(mix_index) if mix_index is not None else None, N, B, M, T,
                                                 _ptr(out), _ptr(means), _ptr(stds), _ptr(work),
                                                 _stream(mix.device)))
-    return out, means.view(N, 1, 1), stds.view(N, 1, 1)
+    return out[:N], means.view(N, 1, 1), stds.view(N, 1, 1)
 
 
 def offsets_to_shifts(offsets):

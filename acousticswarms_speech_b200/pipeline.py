@@ -1,0 +1,95 @@
+"""Batched front end: SRP-PHAT scoring of all hypercubes for a batch of mixtures that share one
+array geometry, MAX_POWER / top-K, and the per-hypercube shift-stack into reused network-batch
+buffers -- the device-resident form of
+    Mic_Array.Apply_SRP_PHAT  ->  Spotform_Big_Patch's shift_and_sep
+(sep/Mic_Array.py:152-222, sep/training/JointModel/network.py:37-104) for B mixtures at once.
+
+The reference processes one mixture at a time and reuses one (128, M, T) device buffer for every
+batch of patches (network.py:58); here a small ring of such buffers is written batch by batch so the
+consumer (the PyTorch separator) can overlap with the next batch's shift-stack.
+"""
+import numpy as np
+import torch
+
+from . import native
+from .constants import SPOT_BATCH_SIZE, window_length
+
+
+class FrontEnd:
+    def __init__(self, srp_node, device=None, net_batch=SPOT_BATCH_SIZE, ring=2, topk=128):
+        """``srp_node``: an ``acousticswarms_speech_b200.srp_phat.SRP_PHAT`` (geometry + device handle)."""
+        self.node = srp_node
+        self.h = srp_node.native
+        self.device = srp_node.device if device is None else torch.device(device)
+        self.net_batch = net_batch
+        self.ring = ring
+        self.topk = topk
+        self._bufs = None
+        self._map = None
+
+    # ---- scoring ---------------------------------------------------------------------------------
+    def score(self, mix_dev):
+        """(B, M, T) float32 CUDA -> (map (B, G), top values (B, K), top indices (B, K))."""
+        B, M, T = mix_dev.shape
+        if self._map is None or self._map.shape[0] != B:
+            self._map = torch.empty((B, self.h.G), device=self.device, dtype=torch.float32)
+        self.h.score(mix_dev, window_length(T), out=self._map)
+        val, idx = native.map_topk(self._map, min(self.topk, 1024))
+        return self._map, val, idx
+
+    # ---- shift-stack -----------------------------------------------------------------------------
+    def _ring(self, M, T):
+        if self._bufs is None or self._bufs[0].shape != (self.net_batch, M, T):
+            self._bufs = [torch.empty((self.net_batch, M, T), device=self.device, dtype=torch.float32)
+                          for _ in range(self.ring)]
+        return self._bufs
+
+    def stack(self, mix_dev, shifts_dev, mix_index_dev, consumer=None, fused_norm=False, events=None):
+        """Write every patch's shifted (M, T) block, ``net_batch`` patches per launch, into the ring.
+        ``consumer(batch_view, first_patch, n)`` stands for the separator; ``events`` (a list) receives
+        (start, end) CUDA event pairs around each shift-stack launch for kernel-level timing."""
+        B, M, T = mix_dev.shape
+        N = shifts_dev.shape[0]
+        bufs = self._ring(M, T)
+        launches = 0
+        for k, i in enumerate(range(0, N, self.net_batch)):
+            n = min(self.net_batch, N - i)
+            buf = bufs[k % self.ring]
+            if events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            if fused_norm:
+                out = native.shift_stack_norm(mix_dev, shifts_dev[i:i + n], mix_index_dev[i:i + n], out=buf)
+                launches += 2
+            else:
+                out = native.shift_stack(mix_dev, shifts_dev[i:i + n], mix_index_dev[i:i + n], out=buf)
+                launches += 1
+            if events is not None:
+                e1.record()
+                events.append((e0, e1, n))
+            if consumer is not None:
+                consumer(out, i, n)
+        return launches
+
+    # ---- host helpers ----------------------------------------------------------------------------
+    def prune_host(self, srp_map_host):
+        """The reference's pruning (SRP_Prunning.py:347-357, 500-643) on one mixture's map -> list[Patch]."""
+        node = self.node
+        node._map_host = np.asarray(srp_map_host)
+        node.SRP_map = torch.from_numpy(node._map_host)
+        node.MAX_POWER = float(node._map_host.max())
+        node.Min_POWER = float(node._map_host.min())
+        node.fill_powermap_torch()
+        return node.local_source_adaptive()
+
+    @staticmethod
+    def patch_table(patch_lists):
+        """list (per mixture) of list[Patch] -> (shifts (N, M) int32, mix_index (N,) int32) numpy."""
+        offs, mi = [], []
+        for b, pl in enumerate(patch_lists):
+            for p in pl:
+                offs.append(p.sample_offset)
+                mi.append(b)
+        if not offs:
+            return np.zeros((0, 1), dtype=np.int32), np.zeros((0,), dtype=np.int32)
+        return native.offsets_to_shifts(np.stack(offs)), np.asarray(mi, dtype=np.int32)

@@ -1,0 +1,77 @@
+"""Shift-and-stack + batched spot-model inference.
+
+Mirror of sep/training/JointModel/network.py: ``roll_by_gather`` (:12-25) and
+``DataParallelSpotModel.shift_and_sep`` (:37-104).  The per-patch Python loop that builds an int64
+index tensor and calls ``torch.gather`` (:80-83) and the separate ``normalize_input`` pass
+(SpeakerLocalization/network.py:28-40) are one fused libasw.so launch per batch.  The network itself
+(the existing PyTorch U-Net/transformer) is untouched: any ``nn.Module`` taking ``(B, M, T)`` and a
+``(B, 2)`` window embedding works.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import native
+from .constants import SPOT_BATCH_SIZE
+
+
+def roll_by_gather(mat, dim, shifts):
+    """out[c, t] = mat[c, (t - shifts[c]) mod T] for dim=1 (network.py:12-25), on the device through
+    the shift-stack kernel.  ``mat`` (rows, cols) float32 CUDA; ``shifts`` LongTensor (rows, 1)."""
+    if dim == 0:
+        return roll_by_gather(mat.t().contiguous(), 1, shifts.reshape(-1, 1)).t().contiguous()
+    r = (-shifts.reshape(1, -1)).to(device=mat.device, dtype=torch.int32).contiguous()
+    return native.shift_stack(mat.contiguous(), r)[0]
+
+
+def unnormalize_input(data, means, stds):
+    """SpeakerLocalization/network.py:42-47."""
+    return data * stds + means
+
+
+class DataParallelSpotModel(nn.Module):
+    def __init__(self, model, use_fp16=False, batch_size=SPOT_BATCH_SIZE, device=None, data_parallel=True):
+        super().__init__()
+        multi = data_parallel and torch.cuda.device_count() > 1
+        self.model = nn.DataParallel(model) if multi else model
+        self.batch_size = batch_size
+        self.dtype = torch.bfloat16 if use_fp16 else torch.float32
+        if use_fp16:
+            self.model.to(torch.bfloat16)
+        self._device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.to(self._device)
+        self._buf = None
+
+    @property
+    def device(self):
+        return self._device
+
+    def shift_and_sep(self, input_channels, patch_list, Strict=0, save_input=False):
+        """network.py:37-104 -> np.ndarray (N, T) float32."""
+        B = self.batch_size
+        N = len(patch_list)
+        dev = self.device
+        self.model.eval()
+        with torch.no_grad():
+            mix = input_channels.to(dev, dtype=torch.float32).contiguous()       # copy once (:55)
+            M, T = mix.shape
+            if self._buf is None or self._buf.shape != (B, M, T):
+                self._buf = torch.empty((B, M, T), device=dev, dtype=torch.float32)   # reused like `data` (:58)
+            results = torch.zeros((N, T), device=dev, dtype=self.dtype)
+            cond = torch.zeros((B, 2), device=dev, dtype=self.dtype)
+            cond[:, 0 if Strict == 1 else 1] = 1                                  # :62-73
+            shifts = torch.from_numpy(native.offsets_to_shifts(
+                np.stack([p.sample_offset for p in patch_list]) if N else np.zeros((0, M - 1)))).to(dev)
+            saved = []
+            for i in range(0, N, B):
+                n = min(B, N - i)
+                data_norm, means, stds = native.shift_stack_norm(mix, shifts[i:i + n], out=self._buf)
+                data_norm = data_norm[:n]
+                if save_input:
+                    saved.append(unnormalize_input(data_norm, means, stds).cpu())
+                result = self.model(data_norm.to(self.dtype), cond[:n])
+                results[i:i + n] = unnormalize_input(result, means.to(self.dtype), stds.to(self.dtype))[:, 0]
+            out = results.cpu().float().numpy()
+        if save_input:
+            return out, (torch.cat(saved) if saved else torch.zeros((0, M, T)))
+        return out

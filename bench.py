@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- TDoA hypercubes scored/sec (SRP-PHAT + shift-stack), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one pass of the hot path over one batch of B synthetic mixtures per GPU, config C2 of
+SURVEY.md section 8d (7 mics, 5 speakers, 3 s @ 48 kHz, one desk geometry, G ~ 2e4 hypercubes):
+    asw_srp_score (STFT+PHAT+cross-spectra -> GCC lag tables -> SRP gather, max over windows)
+    asw_map_topk  (MAX_POWER and the K best hypercubes per mixture)
+    asw_shift_stack of every coarse hypercube patch of every mixture, 128 patches per launch into a
+                  ring of (128, M, T) network-input buffers.
+The coarse patch lists come from the reference's pruning algorithm run on each mixture's map during
+setup (host code, outside the timed region -- GPU pruning is a section-8(f) "next" row).
+`value` starts with inputs resident in HBM; `e2e` starts from pinned host buffers and ends with the
+maps / top-K back on the host.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tdoa_hypercubes_scored_per_sec"
+UNIT = "hypercubes/s"
+WORKLOAD = "C2: coarse width-8 (half-width 4) hypercube SRP-PHAT + Spotform_Big_Patch shift-stack, 7 mics, 5 speakers, 3 s @ 48 kHz"
+N_MICS, N_SPK, T_SAMPLES, FS = 7, 5, 144000, 48000
+GEOM_SEED = 1
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="mixtures per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused-norm", action="store_true", help="shift-stack fused with normalize_input")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_setup():
+    from acousticswarms_speech_b200 import synth
+    from acousticswarms_speech_b200.constants import freq_bins, n_fft
+    from oracle import cpu_reference, geometry_oracle
+    scene = synth.desk_array(N_MICS, np.random.default_rng(GEOM_SEED), FS)
+    geo = geometry_oracle.GeometryOracle(scene.mic_positions, scene.roi)
+    ref = cpu_reference.CpuReferencePath(geo, freq_bins, FS, n_fft)
+    return scene, geo, ref
+
+
+def cpu_reference_step(ref, mix):
+    """One mixture through the reference's CPU path: Apply_SRP_PHAT + the coarse shift loop."""
+    patches, m = ref.apply_srp_phat(mix)
+    ref.shift_stack(mix, patches)
+    return len(patches)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from acousticswarms_speech_b200 import synth
+    scene, geo, ref = cpu_reference_setup()
+    G = geo.grids.shape[0]
+    mixes = [synth.mixture(scene, N_SPK, T_SAMPLES, seed=1000 + i) for i in range(max(1, min(4, args.steps)))]
+    for i in range(max(1, min(args.warmup, 1))):
+        cpu_reference_step(ref, mixes[0])
+    t0 = time.perf_counter()
+    steps = max(1, args.steps)
+    for i in range(steps):
+        cpu_reference_step(ref, mixes[i % len(mixes)])
+    dt = time.perf_counter() - t0
+    v = G * steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "mixtures_per_step": 1, "hypercubes": G,
+                       "note": "reference CPU path (oracle port of SRP_Map_WINDOW_torch + pruning + shift loop), "
+                               "one mixture per step, steering table precomputed (setup excluded, README.md:144)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": ref.threads, "kind": "port",
+                             "sample": f"{steps} mixtures, 1 per step, Apply_SRP_PHAT + coarse shift loop"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    from acousticswarms_speech_b200 import _lib, synth
+    from acousticswarms_speech_b200.constants import SRP_THRESHOLDS, freq_bins, n_fft
+    from acousticswarms_speech_b200.pipeline import FrontEnd
+    from acousticswarms_speech_b200.srp_phat import SRP_PHAT
+
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    scene = synth.desk_array(N_MICS, np.random.default_rng(GEOM_SEED), FS)
+    node = SRP_PHAT(scene.mic_positions, freq_bins, scene.roi, FS=FS, n_fft=n_fft, grid_size=0.05,
+                    threshold=list(SRP_THRESHOLDS), WIDTH=8, device=dev)
+    fe = FrontEnd(node, dev)
+    G = node.grids.shape[0]
+    M, T = N_MICS, T_SAMPLES
+
+    # synthetic mixtures: every rank gets its own B mixtures (weak scaling over mixtures)
+    mix_host = torch.from_numpy(synth.mixtures(scene, N_SPK, T, seeds=[10_000 * rank + 100 + b for b in range(B)]))
+    mix_pin = mix_host.pin_memory()
+    mix_dev = mix_pin.to(dev)
+
+    # setup (untimed): coarse patch lists = the reference's pruning on each mixture's map
+    smap, _, _ = fe.score(mix_dev)
+    torch.cuda.synchronize()
+    maps_h = smap.cpu().numpy()
+    patch_lists = [fe.prune_host(maps_h[b]) for b in range(B)]
+    shifts_np, mi_np = fe.patch_table(patch_lists)
+    N = shifts_np.shape[0]
+    shifts_dev = torch.from_numpy(shifts_np).to(dev)
+    mi_dev = torch.from_numpy(mi_np).to(dev)
+    K = fe.topk
+    map_pin = torch.empty((B, G), dtype=torch.float32).pin_memory()
+    val_pin = torch.empty((B, K), dtype=torch.float32).pin_memory()
+    idx_pin = torch.empty((B, K), dtype=torch.int32).pin_memory()
+    gather_val = [torch.empty((B, K), device=dev) for _ in range(world)] if world > 1 else None
+    gather_idx = [torch.empty((B, K), device=dev, dtype=torch.int32) for _ in range(world)] if world > 1 else None
+
+    def step(events=None, from_host=False):
+        src = mix_dev
+        if from_host:
+            src = mix_pin.to(dev, non_blocking=True)
+        m, val, idx = fe.score(src)
+        if world > 1:          # the one collective of the path: every rank learns every mixture's top-K
+            dist.all_gather(gather_val, val)
+            dist.all_gather(gather_idx, idx)
+        fe.stack(src, shifts_dev, mi_dev, fused_norm=args.fused_norm, events=events)
+        if from_host:
+            map_pin.copy_(m, non_blocking=True)
+            val_pin.copy_(val, non_blocking=True)
+            idx_pin.copy_(idx, non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, from_host, events=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            step(events=events, from_host=from_host)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = _lib.launch_count()
+    ms = timed(args.steps, from_host=False)
+    launches = _lib.launch_count() - l0
+    # kernel-level timing of the dominant kernel (shift-stack) with events on the launching stream
+    events = []
+    timed(max(2, min(args.steps, 5)), from_host=False, events=events)
+    torch.cuda.synchronize()
+    k_ms = [a.elapsed_time(b) for a, b, _ in events]
+    k_bytes = [4.0 * n * M * T for _, _, n in events]
+    full = [(t, by) for t, by in zip(k_ms, k_bytes) if by == 4.0 * fe.net_batch * M * T] or list(zip(k_ms, k_bytes))
+    k_avg_ms = sum(t for t, _ in full) / len(full)
+    k_avg_bytes = sum(by for _, by in full) / len(full)
+    # end to end from pinned host memory
+    for _ in range(2):
+        step(from_host=True)
+    ms_e2e = timed(args.steps, from_host=True)
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk, pk_kind = peaks()
+    per_step = world * B * G
+    value = per_step / (ms / args.steps / 1e3)
+    e2e = per_step / (ms_e2e / args.steps / 1e3)
+    achieved = k_avg_bytes / (k_avg_ms / 1e3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "mixtures_per_gpu_per_step": B, "hypercubes": G, "mics": M, "speakers": N_SPK,
+                   "samples": T, "fs": FS, "coarse_patches_per_step_per_gpu": N, "net_batch": fe.net_batch,
+                   "fused_norm": bool(args.fused_norm), "parallelism": f"mixtures sharded over {world} GPU(s)",
+                   "l2": f"inputs {B * M * T * 4 / 1e6:.0f} MB + stacked output {N * M * T * 4 / 1e9:.2f} GB per step "
+                         "exceed the 126 MB L2 (no explicit flush)",
+                   "prune": "reference algorithm on the host during setup, outside the timed region"},
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(B * M * T * 4), "d2h_bytes_per_step": int(B * G * 4 + B * K * 8)},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "shift_stack_vec_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
+                     "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "peak_kind": pk_kind + " (copy, burst)",
+                     "algorithmic_bytes_per_launch": k_avg_bytes, "avg_launch_ms": k_avg_ms, "traffic": None},
+        "clocks": clocks,
+    }
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as fh:
+                line["roofline"]["traffic"] = json.load(fh).get("shift_stack_vec_kernel_bytes_per_launch")
+        except Exception:
+            pass
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            t0 = time.perf_counter()
+            _, geo, ref = cpu_reference_setup()
+            mixes = mix_host.numpy()
+            cpu_reference_step(ref, mixes[0])                     # warm-up
+            best = None
+            for i in range(3):
+                t1 = time.perf_counter()
+                cpu_reference_step(ref, mixes[(i + 1) % B])
+                dt = time.perf_counter() - t1
+                best = dt if best is None else min(best, dt)
+            line["cpu_baseline"] = {"value": G / best, "unit": UNIT, "cores": ref.threads, "kind": "port",
+                                    "sample": "1 mixture per run (Apply_SRP_PHAT + coarse shift loop), 1 warm-up + best of 3",
+                                    "seconds_per_mixture": best, "setup_seconds_excluded": time.perf_counter() - t0}
+        except Exception as e:  # the CPU leg must never lose the GPU numbers
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"failed: {e!r}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_b200(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

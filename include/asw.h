@@ -127,6 +127,19 @@ int asw_shift_stack_norm(const float* mix_dev, const int32_t* shifts_dev, const 
                          int N, int B, int M, int T, float* out_dev, float* means_dev, float* stds_dev,
                          double* work_dev, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Host-side hypercube table build: SRP_PHAT.Map_3D_TDoA + search_cluster
+ * (sep/Traditional_SP/SRP_Prunning.py:277-344).  Pure CPU code (no device needed).
+ *   offsets [Lx][Ly][Lz][D] int64  quantised TDoA vector of every voxel (:327-331)
+ *   valid   [Lx][Ly][Lz]    uint8  check_valid (:266-275)
+ *   label   [Lx][Ly][Lz]    int32  out: cluster id of the voxel, -1 if invalid
+ *   order   [n_valid]       int32  out: flat voxel indices, cluster-major, members in the
+ *                                  reference's breadth-first order
+ *   cluster_start [n_valid + 1] int32 out: start of each cluster inside `order`
+ * Clusters are numbered in first-seen C-order, exactly like the reference. */
+int asw_geometry_cluster(const int64_t* offsets, const uint8_t* valid, int Lx, int Ly, int Lz, int D,
+                         int32_t* label, int32_t* order, int32_t* cluster_start, int32_t* n_clusters);
+
 #ifdef __cplusplus
 }
 #endif
