@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libasw.so")
 STAMP = os.path.join(LIBDIR, "libasw.stamp")
-SOURCES = ["api.cu", "stft_cc.cu", "gcc.cu", "srp_gather.cu", "topk.cu", "shift_stack.cu", "prune.cu", "geometry.cu"]
+SOURCES = ["api.cu", "stft_cc.cu", "stft_cc_warp.cu", "gcc.cu", "srp_gather.cu", "topk.cu", "shift_stack.cu", "prune.cu", "geometry.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--use_fast_math=false",

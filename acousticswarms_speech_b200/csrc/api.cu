@@ -295,17 +295,30 @@ int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len,
         h->last_Nw = 0;
         return ASW_OK;
     }
-    // frame groups: enough CTAs for ~2 waves when the batch is small, whole windows when it is large
-    int NG = 1;
-    {
-        const long long base = (long long)B * Nw;
-        const long long want = 2LL * kNumSms * 4;  // several CTAs per SM are resident
-        if (base < want) NG = (int)((want + base - 1) / base);
-        if (NG > Nf) NG = Nf;
-        if (NG < 1) NG = 1;
-    }
-    int FG = (Nf + NG - 1) / NG;
-    NG = (Nf + FG - 1) / FG;
+    StftCcParams sp{};
+    sp.mix = mix_dev;
+    sp.tw1024 = h->d_tw1024;
+    sp.twpost = h->d_twpost;
+    sp.B = B;
+    sp.M = h->M;
+    sp.T = T;
+    sp.Nw = Nw;
+    sp.step = win_len / 2;
+    sp.Nf = Nf;
+    sp.bin0 = h->bin0;
+    sp.F = h->F;
+    sp.P = h->P;
+    sp.tol = h->tol;
+    const bool fast = stft_cc_warp_supported(sp);
+    // Frame groups: a CTA owns FG consecutive frames of one (mixture, window) and writes one partial
+    // cross-spectrum.  FG is a constant, NOT a function of the batch size: the order in which frame
+    // products are summed must not depend on how mixtures are batched or sharded across GPUs, so that
+    // B mixtures on one GPU and B/n mixtures on each of n GPUs give bit-identical maps.
+    const int FG = 8;
+    const int NG = (Nf + FG - 1) / FG;
+    (void)fast;
+    sp.NG = NG;
+    sp.FG = FG;
 
     const int wc = Nw < srp_gather_windows_per_chunk() ? Nw : srp_gather_windows_per_chunk();
     if (h->grp_wc != wc) {
@@ -317,24 +330,8 @@ int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len,
     if ((rc = ensure(&h->d_cc, &h->cc_cap, (size_t)B * Nw * h->F * h->P)) != ASW_OK) return rc;
     if ((rc = ensure(&h->d_gcc, &h->gcc_cap, (size_t)B * Nw * h->tab_len)) != ASW_OK) return rc;
 
-    StftCcParams sp{};
-    sp.mix = mix_dev;
     sp.cc_part = h->d_cc_part;
-    sp.tw1024 = h->d_tw1024;
-    sp.twpost = h->d_twpost;
-    sp.B = B;
-    sp.M = h->M;
-    sp.T = T;
-    sp.Nw = Nw;
-    sp.step = win_len / 2;
-    sp.Nf = Nf;
-    sp.NG = NG;
-    sp.FG = FG;
-    sp.bin0 = h->bin0;
-    sp.F = h->F;
-    sp.P = h->P;
-    sp.tol = h->tol;
-    if ((rc = launch_stft_cc(sp, s)) != ASW_OK) return rc;
+    if ((rc = fast ? launch_stft_cc_warp(sp, s) : launch_stft_cc(sp, s)) != ASW_OK) return rc;
 
     GccParams gp{};
     gp.cc_part = h->d_cc_part;

@@ -55,7 +55,10 @@ struct StftCcParams {
     int B, M, T, Nw, step, Nf, NG, FG, bin0, F, P;
     float tol;
 };
-int launch_stft_cc(const StftCcParams& p, cudaStream_t s);
+int launch_stft_cc(const StftCcParams& p, cudaStream_t s);          // generic (any M <= 32)
+bool stft_cc_warp_supported(const StftCcParams& p);                  // fast path: M <= 8, bins in [1, 224)
+int stft_cc_warp_ctas_per_sm(int M);
+int launch_stft_cc_warp(const StftCcParams& p, cudaStream_t s);
 
 struct GccParams {
     const float2* cc_part;  // [B][Nw][NG][F][P]

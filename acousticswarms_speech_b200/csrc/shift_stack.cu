@@ -19,64 +19,33 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kVpt = 4;  // 16-byte vectors per thread
 
-__device__ __forceinline__ int pymod(int a, int n) {
-    int r = a % n;
-    return r < 0 ? r + n : r;
-}
-
 __device__ __forceinline__ float quant16(float x) { return rintf(x * 32768.f) * (1.f / 32768.f); }
 
-// Load 4 consecutive source samples starting at circular position s (0 <= s < T), T % 4 == 0.
-__device__ __forceinline__ float4 load4_circ(const float* __restrict__ src, int s, int T) {
-    if (s + 3 < T) {
-        const int base = s & ~3;
-        const int o = s & 3;
-        const float4 a = __ldg(reinterpret_cast<const float4*>(src + base));
-        if (o == 0) return a;
-        const int nb = (base + 4 < T) ? base + 4 : 0;
-        const float4 c = __ldg(reinterpret_cast<const float4*>(src + nb));
-        if (o == 1) return make_float4(a.y, a.z, a.w, c.x);
-        if (o == 2) return make_float4(a.z, a.w, c.x, c.y);
-        return make_float4(a.w, c.x, c.y, c.z);
-    }
-    float v[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int q = s + i;
-        if (q >= T) q -= T;
-        v[i] = __ldg(src + q);
-    }
-    return make_float4(v[0], v[1], v[2], v[3]);
+__device__ __forceinline__ int reduce_shift(int r, int T) {
+    // python-style r mod T; the common case |r| < T needs no division (the XU pipe was the limiter)
+    if (r <= -T || r >= T) r %= T;
+    return r < 0 ? r + T : r;
 }
 
-template <bool NORM>
-__global__ void __launch_bounds__(kThreads) shift_stack_vec_kernel(const float* __restrict__ mix,
-                                                                    const int32_t* __restrict__ shifts,
-                                                                    const int32_t* __restrict__ mix_index, int M, int T,
-                                                                    float* __restrict__ out,
-                                                                    const double* __restrict__ work,
-                                                                    float* __restrict__ means, float* __restrict__ stds) {
-    const int row = blockIdx.x;  // n * M + c
-    const int n = row / M, c = row - n * M;
-    const int mi = mix_index ? mix_index[n] : 0;
-    const float* src = mix + ((size_t)mi * M + c) * (size_t)T;
-    float4* dst = reinterpret_cast<float4*>(out + (size_t)row * T);
-    const int r = pymod(shifts[row], T);
+// 4 consecutive source samples starting at circular position s = base + O (0 <= s < T, T % 4 == 0,
+// O = s & 3 is the same for a whole row because T and the output position are multiples of 4).
+template <int O>
+__device__ __forceinline__ float4 load4_circ(const float* __restrict__ src, int s, int T) {
+    if (O == 0) return __ldg(reinterpret_cast<const float4*>(src + s));   // aligned, never straddles
+    const int base = s - O;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + base));
+    const int nb = (base + 4 < T) ? base + 4 : 0;                          // wrap of the second vector
+    const float4 c = __ldg(reinterpret_cast<const float4*>(src + nb));
+    if (O == 1) return make_float4(a.y, a.z, a.w, c.x);
+    if (O == 2) return make_float4(a.z, a.w, c.x, c.y);
+    return make_float4(a.w, c.x, c.y, c.z);
+}
+
+template <bool NORM, int O>
+__device__ __forceinline__ void shift_row_chunk(const float* __restrict__ src, float4* __restrict__ dst, int r, int T,
+                                                float mean, float sd) {
     const int T4 = T >> 2;
-    float mean = 0.f, inv_std = 1.f;
-    if (NORM) {
-        const double S = work[2 * n], SS = work[2 * n + 1];
-        const double mu = S / (double)T;
-        const double var = (SS - S * mu) / (double)(T - 1);
-        const float sd = (float)sqrt(var > 0.0 ? var : 0.0);
-        mean = (float)mu;
-        inv_std = sd;  // divide below, like the reference
-        if (c == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-            means[n] = mean;
-            stds[n] = sd;
-        }
-    }
-    const int v0 = blockIdx.y * (kThreads * kVpt) + threadIdx.x;
+    const int v0 = blockIdx.x * (kThreads * kVpt) + threadIdx.x;
     float4 val[kVpt];
 #pragma unroll
     for (int v = 0; v < kVpt; ++v) {
@@ -84,7 +53,7 @@ __global__ void __launch_bounds__(kThreads) shift_stack_vec_kernel(const float* 
         if (t4 < T4) {
             int s = 4 * t4 + r;
             if (s >= T) s -= T;
-            val[v] = load4_circ(src, s, T);
+            val[v] = load4_circ<O>(src, s, T);
         }
     }
 #pragma unroll
@@ -93,13 +62,47 @@ __global__ void __launch_bounds__(kThreads) shift_stack_vec_kernel(const float* 
         if (t4 < T4) {
             float4 x = val[v];
             if (NORM) {
-                x.x = (quant16(x.x) - mean) / inv_std;
-                x.y = (quant16(x.y) - mean) / inv_std;
-                x.z = (quant16(x.z) - mean) / inv_std;
-                x.w = (quant16(x.w) - mean) / inv_std;
+                x.x = (quant16(x.x) - mean) / sd;
+                x.y = (quant16(x.y) - mean) / sd;
+                x.z = (quant16(x.z) - mean) / sd;
+                x.w = (quant16(x.w) - mean) / sd;
             }
             __stcs(dst + t4, x);
         }
+    }
+}
+
+// grid = (chunks of the row, mic c, patch n): no integer division anywhere.
+template <bool NORM>
+__global__ void __launch_bounds__(kThreads) shift_stack_vec_kernel(const float* __restrict__ mix,
+                                                                    const int32_t* __restrict__ shifts,
+                                                                    const int32_t* __restrict__ mix_index, int M, int T,
+                                                                    float* __restrict__ out,
+                                                                    const double* __restrict__ work,
+                                                                    float* __restrict__ means, float* __restrict__ stds) {
+    const int c = blockIdx.y, n = blockIdx.z;
+    const int row = n * M + c;
+    const int mi = mix_index ? mix_index[n] : 0;
+    const float* src = mix + ((size_t)mi * M + c) * (size_t)T;
+    float4* dst = reinterpret_cast<float4*>(out + (size_t)row * T);
+    const int r = reduce_shift(shifts[row], T);
+    float mean = 0.f, sd = 1.f;
+    if (NORM) {
+        const double S = work[2 * n], SS = work[2 * n + 1];
+        const double mu = S / (double)T;
+        const double var = (SS - S * mu) / (double)(T - 1);
+        sd = (float)sqrt(var > 0.0 ? var : 0.0);
+        mean = (float)mu;
+        if (c == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+            means[n] = mean;
+            stds[n] = sd;
+        }
+    }
+    switch (r & 3) {
+        case 0: shift_row_chunk<NORM, 0>(src, dst, r, T, mean, sd); break;
+        case 1: shift_row_chunk<NORM, 1>(src, dst, r, T, mean, sd); break;
+        case 2: shift_row_chunk<NORM, 2>(src, dst, r, T, mean, sd); break;
+        default: shift_row_chunk<NORM, 3>(src, dst, r, T, mean, sd); break;
     }
 }
 
@@ -112,12 +115,12 @@ __global__ void __launch_bounds__(kThreads) shift_stack_scalar_kernel(const floa
                                                                        const double* __restrict__ work,
                                                                        float* __restrict__ means,
                                                                        float* __restrict__ stds) {
-    const int row = blockIdx.x;
-    const int n = row / M, c = row - n * M;
+    const int c = blockIdx.y, n = blockIdx.z;
+    const int row = n * M + c;
     const int mi = mix_index ? mix_index[n] : 0;
     const float* src = mix + ((size_t)mi * M + c) * (size_t)T;
     float* dst = out + (size_t)row * T;
-    const int r = pymod(shifts[row], T);
+    const int r = reduce_shift(shifts[row], T);
     float mean = 0.f, sd = 1.f;
     if (NORM) {
         const double S = work[2 * n], SS = work[2 * n + 1];
@@ -125,12 +128,12 @@ __global__ void __launch_bounds__(kThreads) shift_stack_scalar_kernel(const floa
         const double var = (SS - S * mu) / (double)(T - 1);
         sd = (float)sqrt(var > 0.0 ? var : 0.0);
         mean = (float)mu;
-        if (c == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        if (c == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
             means[n] = mean;
             stds[n] = sd;
         }
     }
-    for (int t = blockIdx.y * (kThreads * kVpt * 4) + threadIdx.x, e = min(T, (int)(blockIdx.y + 1) * (kThreads * kVpt * 4));
+    for (int t = blockIdx.x * (kThreads * kVpt * 4) + threadIdx.x, e = min(T, (int)(blockIdx.x + 1) * (kThreads * kVpt * 4));
          t < e; t += kThreads) {
         int s = t + r;
         if (s >= T) s -= T;
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(kThreads) shift_ref_stats_kernel(const float* 
     const int n = blockIdx.x;
     const int mi = mix_index ? mix_index[n] : 0;
     const float* src = mix + (size_t)mi * M * (size_t)T;
-    if (threadIdx.x < M) s_r[threadIdx.x] = pymod(shifts[n * M + threadIdx.x], T);
+    if (threadIdx.x < M) s_r[threadIdx.x] = reduce_shift(shifts[n * M + threadIdx.x], T);
     __syncthreads();
     const float inv_m = 1.f / (float)M;
     double sum = 0.0, sq = 0.0;
@@ -195,13 +198,22 @@ int launch_rows(const float* mix, const int32_t* shifts, const int32_t* mix_inde
     const bool vec = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(mix) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const int per_cta = kThreads * kVpt * 4;  // samples per CTA
-    dim3 grid((unsigned)(N * M), (unsigned)((T + per_cta - 1) / per_cta));
-    if (vec) {
-        shift_stack_vec_kernel<NORM><<<grid, kThreads, 0, s>>>(mix, shifts, mix_index, M, T, out, work, means, stds);
-        ASW_LAUNCH_CHECK("shift_stack_vec_kernel");
-    } else {
-        shift_stack_scalar_kernel<NORM><<<grid, kThreads, 0, s>>>(mix, shifts, mix_index, M, T, out, work, means, stds);
-        ASW_LAUNCH_CHECK("shift_stack_scalar_kernel");
+    for (int n0 = 0; n0 < N; n0 += 65535) {   // gridDim.z limit
+        const int nn = (N - n0 < 65535) ? N - n0 : 65535;
+        dim3 grid((unsigned)((T + per_cta - 1) / per_cta), (unsigned)M, (unsigned)nn);
+        const int32_t* sh = shifts + (size_t)n0 * M;
+        const int32_t* mi = mix_index ? mix_index + n0 : nullptr;
+        float* o = out + (size_t)n0 * M * T;
+        const double* wk = work ? work + 2 * (size_t)n0 : nullptr;
+        float* mu = means ? means + n0 : nullptr;
+        float* sd = stds ? stds + n0 : nullptr;
+        if (vec) {
+            shift_stack_vec_kernel<NORM><<<grid, kThreads, 0, s>>>(mix, sh, mi, M, T, o, wk, mu, sd);
+            ASW_LAUNCH_CHECK("shift_stack_vec_kernel");
+        } else {
+            shift_stack_scalar_kernel<NORM><<<grid, kThreads, 0, s>>>(mix, sh, mi, M, T, o, wk, mu, sd);
+            ASW_LAUNCH_CHECK("shift_stack_scalar_kernel");
+        }
     }
     return ASW_OK;
 }

@@ -1,0 +1,242 @@
+// stft_cc_warp.cu -- fast path of the fused STFT + PHAT + pair cross-spectra (M <= 8 mics, scored
+// bins inside [1, 224)).  Same arithmetic as stft_cc.cu / the reference
+// (sep/Traditional_SP/SRP_Prunning.py:403-426); different machine mapping:
+//
+//   * one WARP computes one 1024-point complex FFT (the even/odd packed 2048-sample frame) entirely
+//     in registers: lane t holds z[32 q + t], q = 0..31, does a radix-32 DFT over q, applies the
+//     W_1024^{t k1} twiddles, transposes through a padded per-warp shared tile (conflict-free, only
+//     __syncwarp), and does the second radix-32 DFT over t.  Lane k1 then owns Z[k1 + 32 k2].
+//   * only Z[k] for k < 224 and k > 800 feed the scored bins, so the second DFT is pruned to 14 of
+//     its 32 outputs (dead-code elimination of the unrolled butterflies does the pruning).
+//   * the real-input split needs Z[k] and Z[1024 - k]: lane (32 - k1) & 31 holds the partner, fetched
+//     with warp shuffles.
+//   * warp m of the CTA handles mic m; after the M FFTs of a frame one __syncthreads publishes the
+//     PHAT-normalised bins, and thread k accumulates the P pair products of bin k in registers.
+//
+// ncu on the first version (radix-4 x 5 through shared memory, 256 threads per FFT) showed 92 % L1/
+// shared throughput with 60 % of the shared wavefronts being bank-conflict replays; this version moves
+// 8x less data through shared memory per FFT and has no conflicts.
+#include "common.cuh"
+
+namespace asw {
+namespace {
+
+constexpr int kK2 = 7;  // second-pass outputs kept on each side: bins k1 + 32 k2, k2 < 7  (k < 224)
+
+__device__ __forceinline__ constexpr int bitrev5(int x) {
+    return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
+}
+
+// cos(2 pi j / 32), sin(2 pi j / 32), j = 0..15
+__device__ constexpr float kC32[16] = {1.0f,           0.98078528040f, 0.92387953251f, 0.83146961230f,
+                                       0.70710678119f, 0.55557023302f, 0.38268343237f, 0.19509032202f,
+                                       0.0f,           -0.19509032202f, -0.38268343237f, -0.55557023302f,
+                                       -0.70710678119f, -0.83146961230f, -0.92387953251f, -0.98078528040f};
+__device__ constexpr float kS32[16] = {0.0f,           0.19509032202f, 0.38268343237f, 0.55557023302f,
+                                       0.70710678119f, 0.83146961230f, 0.92387953251f, 0.98078528040f,
+                                       1.0f,           0.98078528040f, 0.92387953251f, 0.83146961230f,
+                                       0.70710678119f, 0.55557023302f, 0.38268343237f, 0.19509032202f};
+
+// Forward DFT of 32 register-resident points, radix-2 decimation in frequency, fully unrolled.
+// Output X[k] is left at v[bitrev5(k)].
+__device__ __forceinline__ void dft32(float2 (&v)[32]) {
+#pragma unroll
+    for (int len = 32; len >= 2; len >>= 1) {
+        const int half = len >> 1;
+        const int tstep = 32 / len;  // W_len^j = W_32^{j * tstep}
+#pragma unroll
+        for (int blk = 0; blk < 32; blk += len) {
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+                const float2 a = v[blk + j], b = v[blk + j + half];
+                v[blk + j] = make_float2(a.x + b.x, a.y + b.y);
+                const float dx = a.x - b.x, dy = a.y - b.y;
+                const int tw = j * tstep;  // compile-time after unrolling
+                if (tw == 0) {
+                    v[blk + j + half] = make_float2(dx, dy);
+                } else if (tw == 8) {  // multiply by -i
+                    v[blk + j + half] = make_float2(dy, -dx);
+                } else {
+                    const float c = kC32[tw], s = kS32[tw];  // exp(-i theta) = c - i s
+                    v[blk + j + half] = make_float2(fmaf(dx, c, dy * s), fmaf(dy, c, -dx * s));
+                }
+            }
+        }
+    }
+}
+
+template <int M>
+struct Cfg {
+    static constexpr int kThreads = 32 * M;
+    static constexpr int kP = M * (M - 1) / 2;
+    static constexpr int kNb = (200 + kThreads - 1) / kThreads;  // bins per thread in the pair-product phase
+    static constexpr int kFmax = kThreads * kNb;
+};
+
+template <int M>
+__global__ void __launch_bounds__(32 * M) __maxnreg__((M == 8) ? 128 : 144) stft_cc_warp_kernel(StftCcParams p) {
+    using C = Cfg<M>;
+    extern __shared__ __align__(16) float smem[];
+    // per-warp transpose tile: re[32][33], im[32][33]; then pX double buffer [2][M][F]
+    float* tile = smem + (threadIdx.x >> 5) * (2 * 32 * 33);
+    float2* s_px = reinterpret_cast<float2*>(smem + M * (2 * 32 * 33));
+    const int lane = threadIdx.x & 31;
+    const int m = threadIdx.x >> 5;  // this warp's mic
+    const int tid = threadIdx.x;
+    const int grp = blockIdx.x, w = blockIdx.y, b = blockIdx.z;
+    const int F = p.F;
+
+    // per-lane twiddle seeds W_1024^{t j}, j = 1, 8, 16, 24 (t = lane)
+    const float2 w1 = __ldg(p.tw1024 + lane);
+    const float2 w8 = __ldg(p.tw1024 + ((8 * lane) & 1023));
+    const float2 w16 = __ldg(p.tw1024 + ((16 * lane) & 1023));
+    const float2 w24 = __ldg(p.tw1024 + ((24 * lane) & 1023));
+
+    float2 acc[C::kNb][C::kP];
+#pragma unroll
+    for (int i = 0; i < C::kNb; ++i)
+#pragma unroll
+        for (int q = 0; q < C::kP; ++q) acc[i][q] = make_float2(0.f, 0.f);
+
+    const int n0 = grp * p.FG;
+    const int n1 = min(p.Nf, n0 + p.FG);
+    const float* xm = p.mix + ((size_t)b * p.M + m) * (size_t)p.T + (size_t)w * p.step;
+
+    for (int n = n0; n < n1; ++n) {
+        float2* px = s_px + (size_t)(n & 1) * M * F;
+        {
+            const float* x = xm + (size_t)n * kHop;
+            float2 v[32];
+            if ((reinterpret_cast<uintptr_t>(x) & 7) == 0) {
+                const float2* z = reinterpret_cast<const float2*>(x);
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = __ldg(z + 32 * q + lane);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q)
+                    v[q] = make_float2(__ldg(x + 2 * (32 * q + lane)), __ldg(x + 2 * (32 * q + lane) + 1));
+            }
+            dft32(v);  // Y[k1] at v[bitrev5(k1)]
+            // twiddle by W_1024^{t k1} (re-seeded every 8 steps) and store transposed: tile[k1][t]
+            float2 tw = make_float2(1.f, 0.f);
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1) {
+                if (k1 == 8) tw = w8;
+                if (k1 == 16) tw = w16;
+                if (k1 == 24) tw = w24;
+                const float2 y = (k1 == 0) ? v[0] : cmul(v[bitrev5(k1)], tw);
+                tile[k1 * 33 + lane] = y.x;
+                tile[32 * 33 + k1 * 33 + lane] = y.y;
+                if ((k1 & 7) != 7) tw = cmul(tw, w1);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) v[t] = make_float2(tile[lane * 33 + t], tile[32 * 33 + lane * 33 + t]);
+            __syncwarp();  // tile is rewritten by this warp's next frame
+            dft32(v);      // Z[k1 + 32 k2] at v[bitrev5(k2)], k1 = lane
+            // real-input split for bins k = lane + 32 k2, k2 < kK2, then PHAT
+            const int partner = (32 - lane) & 31;
+#pragma unroll
+            for (int k2 = 0; k2 < kK2; ++k2) {
+                const int k = lane + 32 * k2;
+                const float2 zk = v[bitrev5(k2)];
+                // partner value Z[1024 - k]: lane' = (32 - lane) & 31, k2' = 31 - k2 (lane != 0) or 32 - k2 (lane == 0)
+                const float2 give = v[bitrev5(31 - k2)];
+                float2 zc = make_float2(__shfl_sync(0xffffffffu, give.x, partner),
+                                        __shfl_sync(0xffffffffu, give.y, partner));
+                if (lane == 0) zc = v[bitrev5((32 - k2) & 31)];
+                const int f = k - p.bin0;
+                if (f >= 0 && f < F) {
+                    const float2 post = __ldg(p.twpost + f);
+                    const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+                    const float2 o = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+                    const float2 X = cadd(e, cmul(post, o));
+                    float mag = sqrtf(fmaf(X.x, X.x, X.y * X.y));
+                    mag = fmaxf(mag, p.tol);
+                    const float inv = 1.0f / mag;
+                    px[m * F + f] = make_float2(X.x * inv, X.y * inv);
+                }
+            }
+        }
+        __syncthreads();  // all M mics of frame n are in px
+#pragma unroll
+        for (int i = 0; i < C::kNb; ++i) {
+            const int f = tid + i * C::kThreads;
+            if (f < F) {
+                float2 a[M];
+#pragma unroll
+                for (int mm = 0; mm < M; ++mm) a[mm] = px[mm * F + f];
+                int q = 0;
+#pragma unroll
+                for (int ii = 0; ii < M; ++ii)
+#pragma unroll
+                    for (int jj = ii + 1; jj < M; ++jj) {
+                        acc[i][q].x += fmaf(a[ii].x, a[jj].x, a[ii].y * a[jj].y);
+                        acc[i][q].y += fmaf(a[ii].y, a[jj].x, -a[ii].x * a[jj].y);
+                        ++q;
+                    }
+            }
+        }
+        // no second barrier: frame n+1 writes the other px buffer, and frame n+2 reuses this one only
+        // after the barrier of frame n+1, which every thread reaches after finishing these reads
+    }
+    float2* cc_out = p.cc_part + ((((size_t)b * p.Nw + w) * p.NG + grp) * (size_t)F) * p.P;
+#pragma unroll
+    for (int i = 0; i < C::kNb; ++i) {
+        const int f = tid + i * C::kThreads;
+        if (f < F) {
+#pragma unroll
+            for (int q = 0; q < C::kP; ++q) cc_out[(size_t)f * p.P + q] = acc[i][q];
+        }
+    }
+}
+
+template <int M>
+size_t warp_smem_bytes(int F) {
+    return (size_t)M * (2 * 32 * 33) * sizeof(float) + (size_t)2 * M * F * sizeof(float2);
+}
+
+template <int M>
+int launch_t(const StftCcParams& p, cudaStream_t s) {
+    const size_t smem = warp_smem_bytes<M>(p.F);
+    static bool attr_set = false;
+    if (!attr_set) {
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_warp_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)warp_smem_bytes<M>(200)));
+        attr_set = true;
+    }
+    dim3 grid(p.NG, p.Nw, p.B);
+    stft_cc_warp_kernel<M><<<grid, 32 * M, smem, s>>>(p);
+    ASW_LAUNCH_CHECK("stft_cc_warp_kernel");
+    return ASW_OK;
+}
+
+}  // namespace
+
+bool stft_cc_warp_supported(const StftCcParams& p) {
+    return p.M >= 2 && p.M <= 8 && p.F <= 200 && p.bin0 >= 1 && p.bin0 + p.F <= 32 * kK2;
+}
+
+// resident CTAs per SM of the fast kernel (drives the frame-group choice in api.cu)
+int stft_cc_warp_ctas_per_sm(int M) {
+    const int regs = (M == 8) ? 128 : 144;
+    const int by_regs = 65536 / (32 * M * regs);
+    const int by_smem = (int)((227 * 1024) / (M * (2 * 32 * 33) * sizeof(float) + 2 * M * 200 * sizeof(float2) + 1024));
+    const int n = by_regs < by_smem ? by_regs : by_smem;
+    return n < 1 ? 1 : n;
+}
+
+int launch_stft_cc_warp(const StftCcParams& p, cudaStream_t s) {
+    switch (p.M) {
+        case 2: return launch_t<2>(p, s);
+        case 3: return launch_t<3>(p, s);
+        case 4: return launch_t<4>(p, s);
+        case 5: return launch_t<5>(p, s);
+        case 6: return launch_t<6>(p, s);
+        case 7: return launch_t<7>(p, s);
+        case 8: return launch_t<8>(p, s);
+        default: set_error("stft_cc_warp: unsupported mic count %d", p.M); return ASW_ERR_ARG;
+    }
+}
+
+}  // namespace asw
