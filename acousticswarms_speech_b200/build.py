@@ -16,6 +16,8 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libasw.so")
 STAMP = os.path.join(LIBDIR, "libasw.stamp")
 SOURCES = ["api.cu", "stft_cc.cu", "stft_cc_warp.cu", "gcc.cu", "srp_gather.cu", "topk.cu", "shift_stack.cu", "prune.cu", "geometry.cu"]
+# The warp-FFT kernel needs <= 128 registers/thread so that two CTAs fit the per-partition register files.
+PER_FILE_FLAGS = {"stft_cc_warp.cu": ["-maxrregcount=128"]}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--use_fast_math=false",
@@ -39,6 +41,7 @@ def _digest():
                 h.update(f.encode())
                 h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(repr(sorted(PER_FILE_FLAGS.items())).encode())
     return h.hexdigest()
 
 
@@ -62,7 +65,7 @@ def build_lib(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *flags, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *flags, *PER_FILE_FLAGS.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for cmd, pr in procs:

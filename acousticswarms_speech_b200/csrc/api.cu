@@ -37,6 +37,7 @@ struct asw_srp {
     uint32_t* d_pos = nullptr;   // [P][Gpad] Q12.20
     float2* d_tw1024 = nullptr;  // [1024]
     float2* d_twpost = nullptr;  // [F]
+    float* d_fir = nullptr;      // [(U-1)][12] upsampling weights of gcc.cu
     // staging groups of the gather kernel, one set per window-chunk size
     std::vector<int> grp_begin;
     int* d_grp_begin = nullptr;
@@ -223,6 +224,21 @@ int asw_srp_create(asw_srp_t** out, int device, int M, int G, const double* lag,
         twp[f] = make_float2((float)cos(a), (float)sin(a));
     }
 
+    // 12-tap Lagrange upsampling weights for fractions fr/U, nodes -5..+6 (gcc.cu stage B)
+    std::vector<float> fir((size_t)(U > 1 ? U - 1 : 1) * 12, 0.f);
+    for (int fr = 1; fr < U; ++fr) {
+        const double x = (double)fr / (double)U;
+        for (int a = 0; a < 12; ++a) {
+            double num = 1.0, den = 1.0;
+            for (int c = 0; c < 12; ++c) {
+                if (c == a) continue;
+                num *= x - (double)(c - 5);
+                den *= (double)(a - c);
+            }
+            fir[(size_t)(fr - 1) * 12 + a] = (float)(num / den);
+        }
+    }
+
     int rc = ASW_OK;
     do {
 #define TRY(expr)                                                                          \
@@ -241,6 +257,8 @@ int asw_srp_create(asw_srp_t** out, int device, int M, int G, const double* lag,
         TRY(cudaMalloc(&h->d_pos, sizeof(uint32_t) * pos.size()));
         TRY(cudaMalloc(&h->d_tw1024, sizeof(float2) * kNc));
         TRY(cudaMalloc(&h->d_twpost, sizeof(float2) * h->F));
+        TRY(cudaMalloc(&h->d_fir, sizeof(float) * fir.size()));
+        TRY(cudaMemcpy(h->d_fir, fir.data(), sizeof(float) * fir.size(), cudaMemcpyHostToDevice));
         TRY(cudaMemcpy(h->d_lag_lo, h->lag_lo.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
         TRY(cudaMemcpy(h->d_n_entries, h->n_entries.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
         TRY(cudaMemcpy(h->d_npad, h->npad.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
@@ -268,6 +286,7 @@ int asw_srp_destroy(asw_srp_t* h) {
     cudaFree(h->d_pos);
     cudaFree(h->d_tw1024);
     cudaFree(h->d_twpost);
+    cudaFree(h->d_fir);
     cudaFree(h->d_grp_begin);
     cudaFree(h->d_cc_part);
     cudaFree(h->d_cc);
@@ -341,6 +360,7 @@ int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len,
     gp.n_entries = h->d_n_entries;
     gp.npad = h->d_npad;
     gp.off = h->d_off;
+    gp.fir = h->d_fir;
     gp.B = B;
     gp.Nw = Nw;
     gp.NG = NG;

@@ -68,6 +68,7 @@ struct GccParams {
     const int* n_entries;   // [P] valid entries
     const int* npad;        // [P] entries padded to a multiple of 4
     const int* off;         // [P] float offset of the pair segment (per window unit)
+    const float* fir;       // [(U-1)][12] Lagrange upsampling weights, nodes -5..+6, fraction fr/U
     int B, Nw, NG, F, P, bin0, U, tab_len;
     float inv_nf, scale;    // 1/Nf ; 1/(F*P)
 };

@@ -8,8 +8,14 @@
 //     R_p(l) = 1/(F P) * Re sum_k CC[k, p] exp(+2 pi i k l / nfft).
 // This kernel tabulates R_p on the U-times oversampled lag grid covering the lags the geometry can
 // produce (plus interpolation margin); srp_gather.cu then interpolates.  One CTA per
-// (pair, window, mixture); each entry is a 4-way split Horner evaluation of the polynomial in
-// z = exp(2 pi i l / (nfft U)) with exact integer phase reduction for the seeds.
+// (pair, window, mixture), two stages:
+//   A. R_p at the INTEGER lags (plus a 6-sample margin) into shared memory: each entry is a 4-way
+//      split Horner evaluation of the polynomial in z = exp(2 pi i l / nfft), with exact integer
+//      phase reduction for the seeds;
+//   B. x U upsampling with a fixed 12-tap Lagrange interpolator (weights from the host).  R_p is
+//      band-limited to bin1/nfft < 0.1 cycles/sample, so the 12-tap error (1.6e-6 of the map's max,
+//      measured) is the same as evaluating every fractional lag directly, at 1/U of the work -- ncu
+//      showed the direct version 87 % issue-bound.
 #include "common.cuh"
 
 namespace asw {
@@ -26,12 +32,19 @@ __device__ __forceinline__ float2 cis_turns(int idx, int NU) {
     return make_float2(c, s);
 }
 
+constexpr int kTaps = 12;       // upsampling interpolator length
+constexpr int kMargin = 5;      // nodes -5 .. +6 around the integer lag below the target
+constexpr int kMaxInt = kMaxEntries + kTaps + 4;
+
 __global__ void __launch_bounds__(kThreads) gcc_kernel(GccParams p) {
     __shared__ float2 s_c[kMaxBins + 4];
+    __shared__ float s_r1[kMaxInt];
+    __shared__ float s_fir[7 * kTaps];
     const int tid = threadIdx.x;
     const int pr = blockIdx.x, w = blockIdx.y, b = blockIdx.z;
     const int F = p.F;
     const int Fpad = (F + 3) & ~3;
+    const int U = p.U;
 
     for (int f = tid; f < Fpad; f += kThreads) {
         float2 s = make_float2(0.f, 0.f);
@@ -48,32 +61,48 @@ __global__ void __launch_bounds__(kThreads) gcc_kernel(GccParams p) {
         }
         s_c[f] = s;
     }
+    for (int i = tid; i < (U - 1) * kTaps; i += kThreads) s_fir[i] = p.fir[i];
     __syncthreads();
 
     const int lo = p.lag_lo[pr], n = p.n_entries[pr], npd = p.npad[pr];
     float* out = p.gcc + (size_t)b * p.tab_len * p.Nw + (size_t)p.Nw * p.off[pr] + (size_t)w * npd;
-    const int NU = kNfft * p.U;
     const int nch = Fpad >> 2;
+    const int n_int = (n - 1) / U + 1 + kTaps;   // integer lags lo - kMargin ... hi + 6
 
+    // stage A: integer lags
+    for (int j = tid; j < n_int; j += kThreads) {
+        const int L = lo - kMargin + j;
+        const float2 z = cis_turns(L, kNfft);
+        const float2 z4 = cis_turns(4 * L, kNfft);
+        const float2 zk = cis_turns(p.bin0 * L, kNfft);
+        float2 a0 = s_c[4 * (nch - 1)], a1 = s_c[4 * (nch - 1) + 1];
+        float2 a2 = s_c[4 * (nch - 1) + 2], a3 = s_c[4 * (nch - 1) + 3];
+        for (int m = nch - 2; m >= 0; --m) {
+            a0 = cadd(cmul(a0, z4), s_c[4 * m]);
+            a1 = cadd(cmul(a1, z4), s_c[4 * m + 1]);
+            a2 = cadd(cmul(a2, z4), s_c[4 * m + 2]);
+            a3 = cadd(cmul(a3, z4), s_c[4 * m + 3]);
+        }
+        float2 t = cadd(a2, cmul(z, a3));
+        t = cadd(a1, cmul(z, t));
+        t = cadd(a0, cmul(z, t));
+        s_r1[j] = (zk.x * t.x - zk.y * t.y) * p.scale;
+    }
+    __syncthreads();
+
+    // stage B: x U upsampling; entry i is lag lo + i / U
     for (int i = tid; i < npd; i += kThreads) {
         float val = 0.f;
         if (i < n) {
-            const int L = lo * p.U + i;
-            const float2 z = cis_turns(L, NU);
-            const float2 z4 = cis_turns(4 * L, NU);
-            const float2 zk = cis_turns(p.bin0 * L, NU);
-            float2 a0 = s_c[4 * (nch - 1)], a1 = s_c[4 * (nch - 1) + 1];
-            float2 a2 = s_c[4 * (nch - 1) + 2], a3 = s_c[4 * (nch - 1) + 3];
-            for (int m = nch - 2; m >= 0; --m) {
-                a0 = cadd(cmul(a0, z4), s_c[4 * m]);
-                a1 = cadd(cmul(a1, z4), s_c[4 * m + 1]);
-                a2 = cadd(cmul(a2, z4), s_c[4 * m + 2]);
-                a3 = cadd(cmul(a3, z4), s_c[4 * m + 3]);
+            const int j = i / U, fr = i - j * U;
+            const float* r = s_r1 + j;              // r[kMargin] is the integer lag at or below the target
+            if (fr == 0) {
+                val = r[kMargin];
+            } else {
+                const float* wt = s_fir + (fr - 1) * kTaps;
+#pragma unroll
+                for (int t = 0; t < kTaps; ++t) val = fmaf(wt[t], r[t], val);
             }
-            float2 t = cadd(a2, cmul(z, a3));
-            t = cadd(a1, cmul(z, t));
-            t = cadd(a0, cmul(z, t));
-            val = (zk.x * t.x - zk.y * t.y) * p.scale;
         }
         out[i] = val;
     }
@@ -85,6 +114,10 @@ int launch_gcc(const GccParams& p, cudaStream_t s) {
     if (p.F > kMaxBins) {
         set_error("gcc: %d scored bins exceed the kernel limit of %d", p.F, kMaxBins);
         return ASW_ERR_RANGE;
+    }
+    if (p.U < 1 || p.U > 8) {
+        set_error("gcc: oversampling %d unsupported", p.U);
+        return ASW_ERR_ARG;
     }
     dim3 grid(p.P, p.Nw, p.B);
     gcc_kernel<<<grid, kThreads, 0, s>>>(p);

@@ -16,7 +16,7 @@
 namespace asw {
 namespace {
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 1024;           // 32 warps hide the shared-memory gather latency (ncu: short_scoreboard)
 constexpr int kWc = 8;                    // windows per staging chunk
 constexpr int kSmemBudget = 200 * 1024;   // bytes of GCC table staged at once
 
@@ -124,8 +124,6 @@ int launch_srp_gather(const SrpGatherParams& p, cudaStream_t s) {
         return ASW_ERR_RANGE;
     }
     // Larger tiles amortise the table staging; smaller tiles fill the 148 SMs when the batch is small.
-    const long long tiles4 = (long long)((p.G + kThreads * 4 - 1) / (kThreads * 4)) * p.B;
-    if (tiles4 >= 2 * kNumSms) return launch_t<4>(p, s);
     const long long tiles2 = (long long)((p.G + kThreads * 2 - 1) / (kThreads * 2)) * p.B;
     if (tiles2 >= kNumSms) return launch_t<2>(p, s);
     return launch_t<1>(p, s);

@@ -74,7 +74,8 @@ struct Cfg {
 };
 
 template <int M>
-__global__ void __launch_bounds__(32 * M) __maxnreg__((M == 8) ? 128 : 144) stft_cc_warp_kernel(StftCcParams p) {
+// no __launch_bounds__ here: it would override the per-file -maxrregcount=128 (see build.py)
+__global__ void stft_cc_warp_kernel(StftCcParams p) {
     using C = Cfg<M>;
     extern __shared__ __align__(16) float smem[];
     // per-warp transpose tile: re[32][33], im[32][33]; then pX double buffer [2][M][F]
@@ -203,6 +204,9 @@ int launch_t(const StftCcParams& p, cudaStream_t s) {
     if (!attr_set) {
         ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_warp_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)warp_smem_bytes<M>(200)));
+        // without this the driver may pick a carve-out that fits only one CTA (ncu: occupancy limit 1)
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_warp_kernel<M>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            (int)cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     dim3 grid(p.NG, p.Nw, p.B);
@@ -219,8 +223,8 @@ bool stft_cc_warp_supported(const StftCcParams& p) {
 
 // resident CTAs per SM of the fast kernel (drives the frame-group choice in api.cu)
 int stft_cc_warp_ctas_per_sm(int M) {
-    const int regs = (M == 8) ? 128 : 144;
-    const int by_regs = 65536 / (32 * M * regs);
+    // registers are allocated per SM sub-partition (16K each): 128 regs/thread = 4 warps per partition
+    const int by_regs = 16 / M;
     const int by_smem = (int)((227 * 1024) / (M * (2 * 32 * 33) * sizeof(float) + 2 * M * 200 * sizeof(float2) + 1024));
     const int n = by_regs < by_smem ? by_regs : by_smem;
     return n < 1 ? 1 : n;
