@@ -74,13 +74,8 @@ class FrontEnd:
     # ---- host helpers ----------------------------------------------------------------------------
     def prune_host(self, srp_map_host):
         """The reference's pruning (SRP_Prunning.py:347-357, 500-643) on one mixture's map -> list[Patch]."""
-        node = self.node
-        node._map_host = np.asarray(srp_map_host)
-        node.SRP_map = torch.from_numpy(node._map_host)
-        node.MAX_POWER = float(node._map_host.max())
-        node.Min_POWER = float(node._map_host.min())
-        node.fill_powermap_torch()
-        return node.local_source_adaptive()
+        self.node.load_map(srp_map_host)
+        return self.node.local_source_adaptive()
 
     @staticmethod
     def patch_table(patch_lists):

