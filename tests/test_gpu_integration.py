@@ -1,0 +1,156 @@
+"""GPU: the drop-in classes end to end -- Mic_Array.Apply_SRP_PHAT, shift_and_sep, the batched front
+end -- against the reference's golden vectors and the oracle, plus size-independent properties at
+BASELINE.json's full sizes."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from acousticswarms_speech_b200 import constants, native, synth
+from oracle import prune_oracle, shift_oracle, srp_oracle
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-4           # fp32 vs the reference, normwise (north_star)
+TIE = 2e-5           # index sets may differ only at near-ties within ~1e-5 relative
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def decision_margin(node, gmap, max_power):
+    """Per cluster: how close (relative) any of its interior voxels is to flipping a comparison of
+    find_valid_peak_new (SRP_Prunning.py:500-544) -- used to accept near-tie differences only."""
+    pm, pi = prune_oracle.fill_powermap(gmap, [(None, None, c.index) for c in node.clusters],
+                                        (node.Lx, node.Ly, node.Lz))
+    t1, t2 = prune_oracle.adaptive_thresholds(max_power)
+    NX, NY, NZ = pm.shape
+    core = pm[2:-2, 2:-2, 1:-1]
+    th1 = (t1 * (0.9 + 1 / node.dis_matrix))[2:-2, 2:-2, None]
+    th2 = (t2 * (1 + 1 / node.dis_matrix))[2:-2, 2:-2, None]
+    nb = None
+    for dx in range(-2, 3):
+        for dy in range(-2, 3):
+            for dz in (-1, 0):
+                if dx == dy == dz == 0:
+                    continue
+                v = pm[2 + dx:NX - 2 + dx, 2 + dy:NY - 2 + dy, 1 + dz:NZ - 1 + dz]
+                d = np.abs(core - v)
+                d[v == core] = np.inf          # exact plateaus (same cluster) are not ties between clusters
+                nb = d if nb is None else np.minimum(nb, d)
+    m = np.minimum(nb, np.minimum(np.abs(core - th1), np.abs(core - th2))) / np.maximum(core, 1e-12)
+    out = np.full(len(node.clusters), np.inf)
+    ids = pi[2:-2, 2:-2, 1:-1]
+    np.minimum.at(out, ids.ravel(), m.ravel())
+    return out
+
+
+@pytest.fixture(scope="module")
+def desk():
+    g = np.load(os.path.join(GOLDEN, "desk_scene.npz"))
+    scene = synth.Scene(g["mic_positions"], list(g["roi"]), int(g["fs"]))
+    mix = synth.mixture(scene, int(g["n_spk"]), int(g["T"]), int(g["seed"]))
+    if sha(mix) != str(g["mix_sha"]):
+        pytest.skip("synthetic generator stream differs from the fixture's")
+    from acousticswarms_speech_b200.mic_array import Mic_Array
+    ma = Mic_Array(scene.mic_positions, Spk_Range=scene.roi)
+    return g, scene, mix, ma
+
+
+def test_apply_srp_phat_matches_reference_golden(cuda_device, desk):
+    g, scene, mix, ma = desk
+    patches, simple_pos = ma.Apply_SRP_PHAT(torch.from_numpy(mix))
+    node = ma.SRP_node
+    assert simple_pos.shape == (3, 3) and not simple_pos.any()
+    got = node.SRP_map.cpu().numpy()
+    ref = g["srp_map"]
+    assert np.abs(got - ref).max() <= TOL * ref.max()
+    assert abs(node.MAX_POWER - float(g["max_power"])) <= TOL * float(g["max_power"])
+    # pruned hypercube index set: identical except for near-ties
+    peaks = node.find_valid_peak_new()
+    want = [int(i) for i in g["peaks"]]
+    diff = set(peaks) ^ set(want)
+    if diff:
+        margin = decision_margin(node, ref, float(g["max_power"]))
+        assert all(margin[i] < TIE for i in diff), f"peak sets differ beyond near-ties: {sorted(diff)}"
+    else:
+        assert peaks == want
+        assert np.array_equal(np.array([p.sample_offset for p in patches]), g["patch_offsets"])
+        assert np.array_equal(np.array([p.width_list for p in patches]), g["patch_widths"])
+        assert [p.area_size() for p in patches] == list(g["patch_area_sizes"])
+
+
+class MeanOverMics(torch.nn.Module):
+    """Stand-in for the spot network: (B, M, T), (B, 2) -> (B, 1, T)."""
+
+    def forward(self, x, cond):
+        return x.mean(1, keepdim=True) * cond[:, 1:2].unsqueeze(-1) + 2 * x[:, :1] * cond[:, 0:1].unsqueeze(-1)
+
+
+def test_shift_and_sep_drop_in(cuda_device, desk):
+    g, scene, mix, ma = desk
+    from acousticswarms_speech_b200.spot import DataParallelSpotModel
+    spot = DataParallelSpotModel(MeanOverMics(), batch_size=16)
+    patches = [prune_oracle.Patch(o, w, None) for o, w in zip(g["patch_offsets"], g["patch_widths"])]   # 39 -> 3 batches
+    for strict in (0, 1):
+        out = spot.shift_and_sep(torch.from_numpy(mix), patches, Strict=strict)
+        assert out.shape == (len(patches), mix.shape[1]) and out.dtype == np.float32
+        stacked = shift_oracle.shift_stack(mix, [p.sample_offset for p in patches])
+        dn, mu, sd = shift_oracle.normalize_input(stacked)
+        net = dn.mean(1) if strict == 0 else 2 * dn[:, 0]
+        want = net * sd[:, 0] + mu[:, 0]
+        assert np.abs(out - want).max() <= TOL * np.abs(want).max()
+    assert spot.shift_and_sep(torch.from_numpy(mix), [], Strict=0).shape == (0, mix.shape[1])
+
+
+def test_roll_by_gather_drop_in(cuda_device):
+    from acousticswarms_speech_b200.spot import roll_by_gather
+    rng = np.random.default_rng(1)
+    mat = rng.standard_normal((6, 5000)).astype(np.float32)
+    sh = torch.tensor([[0], [3], [-7], [4999], [-5000], [12345]])
+    got = roll_by_gather(torch.from_numpy(mat).cuda(), 1, sh).cpu().numpy()
+    assert np.array_equal(got, shift_oracle.roll_by_gather(mat, sh.numpy().ravel()))
+
+
+def test_front_end_batch_equals_per_mixture(cuda_device, desk):
+    g, scene, mix, ma = desk
+    from acousticswarms_speech_b200.pipeline import FrontEnd
+    fe = FrontEnd(ma.SRP_node, topk=32)
+    mixes = np.stack([mix, synth.mixture(scene, 5, mix.shape[1], seed=77), mix[::-1].copy()])
+    smap, val, idx = fe.score(torch.from_numpy(mixes).cuda())
+    smap = smap.cpu().numpy()
+    ma.Apply_SRP_PHAT(torch.from_numpy(mix))
+    assert np.array_equal(smap[0], ma.SRP_node.SRP_map.cpu().numpy())     # batch-shape independent
+    assert np.array_equal(idx.cpu().numpy()[:, 0], smap.argmax(1))
+    assert np.array_equal(val.cpu().numpy()[:, 0], smap.max(1))
+    patch_lists = [fe.prune_host(smap[b]) for b in range(3)]
+    shifts, mi = fe.patch_table(patch_lists)
+    seen = []
+    fe.net_batch = 16
+    fe.stack(torch.from_numpy(mixes).cuda(), torch.from_numpy(shifts).cuda(), torch.from_numpy(mi).cuda(),
+             consumer=lambda out, first, n: seen.append((first, out[:n].cpu().numpy())))
+    assert sum(o.shape[0] for _, o in seen) == shifts.shape[0]
+    for first, out in seen:
+        for j in range(out.shape[0]):
+            n = first + j
+            assert np.array_equal(out[j], shift_oracle.roll_by_gather(mixes[mi[n]], -shifts[n].astype(np.int64)))
+
+
+def test_full_size_properties(cuda_device, desk):
+    """BASELINE-size properties that need no oracle run: PHAT makes the map invariant to per-channel
+    gain; a single broadband source puts the map's maximum on the hypercube holding its true TDoAs."""
+    g, scene, mix, ma = desk
+    h = ma.SRP_node.native
+    x = torch.from_numpy(mix).cuda()
+    base = h.score(x, 36000).clone()
+    gains = torch.tensor([1.0, 0.5, 2.0, 4.0, 0.25, 8.0, 1.0], device=x.device).view(-1, 1)   # powers of two: exact
+    assert torch.equal(h.score(x * gains, 36000), base)
+    one, spk = synth.mixture(scene, 1, 144000, seed=5, return_sources=True)
+    m = h.score(torch.from_numpy(one).cuda(), 36000)[0].cpu().numpy()
+    true = synth.true_offsets(scene, spk)[0]
+    best = ma.SRP_node.clusters[int(m.argmax())].sample_offset
+    assert np.abs(best - true).max() <= 4.0, (best, true)
+    assert m.max() > 0.5            # a single coherent source scores near 1
