@@ -65,6 +65,34 @@ __device__ __forceinline__ void dft32(float2 (&v)[32]) {
     }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// Asynchronously copy one 2048-sample frame (8 KB, contiguous) into this warp's tile, raw layout.
+__device__ __forceinline__ void prefetch_frame(float* tile, const float* x, int lane) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(x);
+    if ((a & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) cp_async16(tile + 4 * (lane + 32 * j), x + 4 * (lane + 32 * j));
+    } else if ((a & 7) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cp_async8(tile + 2 * (lane + 32 * j), x + 2 * (lane + 32 * j));
+    } else {
+#pragma unroll 8
+        for (int j = 0; j < 64; ++j) cp_async4(tile + (lane + 32 * j), x + (lane + 32 * j));
+    }
+    cp_async_commit();
+}
+
 template <int M>
 struct Cfg {
     static constexpr int kThreads = 32 * M;
@@ -103,20 +131,23 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
     const int n1 = min(p.Nf, n0 + p.FG);
     const float* xm = p.mix + ((size_t)b * p.M + m) * (size_t)p.T + (size_t)w * p.step;
 
+    // The tile is idle between the transposed read of frame n and the transposed write of frame n+1:
+    // it doubles as the landing buffer of the cp.async prefetch of frame n+1 (raw layout, 8 KB), so
+    // the global-load latency overlaps the second DFT pass, the split/PHAT and the pair products.
+    if (n0 < n1) prefetch_frame(tile, xm + (size_t)n0 * kHop, lane);
+
     for (int n = n0; n < n1; ++n) {
         float2* px = s_px + (size_t)(n & 1) * M * F;
         {
-            const float* x = xm + (size_t)n * kHop;
             float2 v[32];
-            if ((reinterpret_cast<uintptr_t>(x) & 7) == 0) {
-                const float2* z = reinterpret_cast<const float2*>(x);
+            cp_async_wait_all();
+            __syncwarp();
+            {
+                const float2* raw = reinterpret_cast<const float2*>(tile);
 #pragma unroll
-                for (int q = 0; q < 32; ++q) v[q] = __ldg(z + 32 * q + lane);
-            } else {
-#pragma unroll
-                for (int q = 0; q < 32; ++q)
-                    v[q] = make_float2(__ldg(x + 2 * (32 * q + lane)), __ldg(x + 2 * (32 * q + lane) + 1));
+                for (int q = 0; q < 32; ++q) v[q] = raw[32 * q + lane];   // z[t] = x[2t] + i x[2t+1]
             }
+            __syncwarp();  // every lane has its raw samples before the tile is overwritten
             dft32(v);  // Y[k1] at v[bitrev5(k1)]
             // twiddle by W_1024^{t k1} (re-seeded every 8 steps) and store transposed: tile[k1][t]
             float2 tw = make_float2(1.f, 0.f);
@@ -133,7 +164,8 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
             __syncwarp();
 #pragma unroll
             for (int t = 0; t < 32; ++t) v[t] = make_float2(tile[lane * 33 + t], tile[32 * 33 + lane * 33 + t]);
-            __syncwarp();  // tile is rewritten by this warp's next frame
+            __syncwarp();  // the tile is free again: start fetching the next frame into it
+            if (n + 1 < n1) prefetch_frame(tile, xm + (size_t)(n + 1) * kHop, lane);
             dft32(v);      // Z[k1 + 32 k2] at v[bitrev5(k2)], k1 = lane
             // real-input split for bins k = lane + 32 k2, k2 < kK2, then PHAT
             const int partner = (32 - lane) & 31;
@@ -192,6 +224,10 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
     }
 }
 
+}  // namespace
+int stft_cc_warp_ctas_per_sm(int M);
+namespace {
+
 template <int M>
 size_t warp_smem_bytes(int F) {
     return (size_t)M * (2 * 32 * 33) * sizeof(float) + (size_t)2 * M * F * sizeof(float2);
@@ -205,8 +241,11 @@ int launch_t(const StftCcParams& p, cudaStream_t s) {
         ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_warp_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)warp_smem_bytes<M>(200)));
         // without this the driver may pick a carve-out that fits only one CTA (ncu: occupancy limit 1)
-        ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_warp_kernel<M>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                            (int)cudaSharedmemCarveoutMaxShared));
+        // just enough shared memory for the resident CTAs, the rest stays L1
+        const int ctas = stft_cc_warp_ctas_per_sm(M);
+        int pct = (int)((ctas * (warp_smem_bytes<M>(200) + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
+        if (pct > 100) pct = 100;
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_warp_kernel<M>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         attr_set = true;
     }
     dim3 grid(p.NG, p.Nw, p.B);

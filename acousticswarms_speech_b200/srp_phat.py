@@ -43,12 +43,23 @@ class Grid_cluster(object):
         return [self.sample_offset, self.grids, self.index]
 
 
-def hyperbola_offset(offset, pos, sample_offsets, width):
-    """Points whose TDoA vector lies inside the closed box (SRP_Prunning.py:19-28)."""
-    z = np.ones(offset.shape[:-1], dtype=bool)
-    for i in range(offset.shape[-1]):
-        z &= (offset[..., i] >= sample_offsets[i] - width / 2) & (offset[..., i] <= sample_offsets[i] + width / 2)
-    return pos[z]
+def hyperbola_offset(offset, pos, sample_offsets, width, first=None):
+    """Points whose TDoA vector lies inside the closed box (SRP_Prunning.py:19-28).
+
+    Same comparisons as the reference, evaluated progressively: dimension 0 on every voxel (``first``:
+    an optional contiguous copy of ``offset[..., 0]``), the remaining dimensions only on the survivors.
+    ``np.nonzero`` enumerates in C order, so the returned points are in the reference's order.  This
+    scan is 0.2 s of the reference's 0.23 s pruning time."""
+    D = offset.shape[-1]
+    f = offset[..., 0] if first is None else first
+    idx = np.nonzero((f >= sample_offsets[0] - width / 2) & (f <= sample_offsets[0] + width / 2))
+    for i in range(1, D):
+        if idx[0].size == 0:
+            break
+        v = offset[idx + (i,)]
+        keep = (v >= sample_offsets[i] - width / 2) & (v <= sample_offsets[i] + width / 2)
+        idx = tuple(a[keep] for a in idx)
+    return pos[idx]
 
 
 def hyperbola_area_sample(sample_list, sample_offsets, width):
@@ -58,9 +69,9 @@ def hyperbola_area_sample(sample_list, sample_offsets, width):
     return np.all((sample_list >= lo) & (sample_list <= hi), axis=1).astype(int)
 
 
-def hyperbola_area_init(Axis_range, sample_offsets, width, Pos5, Offset5, Pos1, Offset1):
+def hyperbola_area_init(Axis_range, sample_offsets, width, Pos5, Offset5, Pos1, Offset1, first5=None, first1=None):
     """5 cm probe, then the 1 cm voxels inside the box, as (3, n) (SRP_Prunning.py:41-61)."""
-    pts = hyperbola_offset(Offset5, Pos5, sample_offsets, width)
+    pts = hyperbola_offset(Offset5, Pos5, sample_offsets, width, first5)
     if pts.shape[0] == 0:
         return None
     x_min = max([Axis_range[0][0], pts[:, 0].min() - 0.05])
@@ -71,7 +82,8 @@ def hyperbola_area_init(Axis_range, sample_offsets, width, Pos5, Offset5, Pos1, 
     y_max = min([Axis_range[1][1], pts[:, 1].max() + 0.05])
     iy0 = int(np.floor((y_min - Axis_range[1][0]) / 0.01))
     iy1 = int(np.ceil((y_max - Axis_range[1][0]) / 0.01))
-    pts = hyperbola_offset(Offset1[iy0:iy1, ix0:ix1, :, :], Pos1[iy0:iy1, ix0:ix1, :, :], sample_offsets, width)
+    pts = hyperbola_offset(Offset1[iy0:iy1, ix0:ix1, :, :], Pos1[iy0:iy1, ix0:ix1, :, :], sample_offsets, width,
+                           None if first1 is None else first1[iy0:iy1, ix0:ix1, :])
     return pts.T
 
 
@@ -176,6 +188,16 @@ class SRP_PHAT(object):
                 out += [pos, offs]
             self._fine = out
         return self._fine
+
+    def _first5(self):
+        if getattr(self, "_first5_cache", None) is None:
+            self._first5_cache = np.ascontiguousarray(self.Offset_5[..., 0])
+        return self._first5_cache
+
+    def _first1(self):
+        if getattr(self, "_first1_cache", None) is None:
+            self._first1_cache = np.ascontiguousarray(self.Offset_1[..., 0])
+        return self._first1_cache
 
     Pos_5 = property(lambda self: self._fine_volumes()[0])
     Offset_5 = property(lambda self: self._fine_volumes()[1])
@@ -347,7 +369,7 @@ class SRP_PHAT(object):
             widths = np.array(widths)
             centres = np.array(centres)
             area = hyperbola_area_init(self.Axis_range, centres, widths[0] + ERR_TOLERANCE, self.Pos_5,
-                                       self.Offset_5, self.Pos_1, self.Offset_1)
+                                       self.Offset_5, self.Pos_1, self.Offset_1, self._first5(), self._first1())
             if area is None or area.shape[-1] == 0:
                 continue
             patch_candidate.append(Patch(centres, widths, area, candidate))

@@ -19,9 +19,7 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -57,53 +55,60 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons of one GPU every few ms over the timed regions (NVML in a
+    thread; the timed regions last tens of ms, too short for `nvidia-smi -lms`)."""
 
-    def __init__(self, gpu_index=0):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    def __init__(self, gpu_index=0, period_s=0.004):
+        import threading
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._ok = False
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._ok = True
         except Exception:
-            self.p = None
+            return
+        self._period = period_s
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def _run(self):
+        nv = self._nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self._period)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        if not self._ok:
             return out
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
-        if sm:
-            out["sm_mhz"] = statistics.median(sm)
-            out["sm_max_mhz"] = max(mx)
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
+        self._stop.set()
+        self._t.join(timeout=2)
+        if self.samples:
+            out["sm_mhz"] = statistics.median(self.samples)
+            out["samples"] = len(self.samples)
+        out["reasons"] = sorted(self.reasons)
         return out
 
 
@@ -196,16 +201,13 @@ def run_b200(args, rank, world):
     gather_val = [torch.empty((B, K), device=dev) for _ in range(world)] if world > 1 else None
     gather_idx = [torch.empty((B, K), device=dev, dtype=torch.int32) for _ in range(world)] if world > 1 else None
 
-    def step(events=None, from_host=False):
-        src = mix_dev
-        if from_host:
-            src = mix_pin.to(dev, non_blocking=True)
+    def compute(src, events=None, to_host=False):
         m, val, idx = fe.score(src)
         if world > 1:          # the one collective of the path: every rank learns every mixture's top-K
             dist.all_gather(gather_val, val)
             dist.all_gather(gather_idx, idx)
         fe.stack(src, shifts_dev, mi_dev, fused_norm=args.fused_norm, events=events)
-        if from_host:
+        if to_host:
             map_pin.copy_(m, non_blocking=True)
             val_pin.copy_(val, non_blocking=True)
             idx_pin.copy_(idx, non_blocking=True)
@@ -216,30 +218,67 @@ def run_b200(args, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n_steps, from_host, events=None):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n_steps):
-            step(events=events, from_host=from_host)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
+    def reduce_max_ms(ms):
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
 
+    def timed(n_steps, events=None):
+        """value: inputs already resident in HBM."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            compute(mix_dev, events=events)
+        e1.record()
+        barrier()
+        return reduce_max_ms(e0.elapsed_time(e1))
+
+    # e2e: every step copies its B mixtures from pinned host memory (double-buffered on a copy stream so
+    # the PCIe transfer of step i+1 overlaps the kernels of step i) and returns maps + top-K to the host.
+    copy_stream = torch.cuda.Stream(device=dev)
+    in_bufs = [torch.empty_like(mix_dev), torch.empty_like(mix_dev)]
+
+    def timed_e2e(n_steps):
+        barrier()
+        main = torch.cuda.current_stream(dev)
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        copy_stream.wait_event(e0)
+        with torch.cuda.stream(copy_stream):
+            in_bufs[0].copy_(mix_pin, non_blocking=True)
+            copied[0].record()
+        for i in range(n_steps):
+            cur, nxt = i & 1, (i + 1) & 1
+            if i + 1 < n_steps:
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(consumed[nxt])
+                    in_bufs[nxt].copy_(mix_pin, non_blocking=True)
+                    copied[nxt].record()
+            main.wait_event(copied[cur])
+            compute(in_bufs[cur], to_host=True)
+            consumed[cur].record()
+        e1.record()
+        barrier()
+        return reduce_max_ms(e0.elapsed_time(e1))
+
+    def step():
+        compute(mix_dev)
+
     for _ in range(max(args.warmup, 3)):
         step()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = _lib.launch_count()
-    ms = timed(args.steps, from_host=False)
+    ms = timed(args.steps)
     launches = _lib.launch_count() - l0
     # kernel-level timing of the dominant kernel (shift-stack) with events on the launching stream
     events = []
-    timed(max(2, min(args.steps, 5)), from_host=False, events=events)
+    timed(max(2, min(args.steps, 5)), events=events)
     torch.cuda.synchronize()
     k_ms = [a.elapsed_time(b) for a, b, _ in events]
     k_bytes = [4.0 * n * M * T for _, _, n in events]
@@ -247,9 +286,8 @@ def run_b200(args, rank, world):
     k_avg_ms = sum(t for t, _ in full) / len(full)
     k_avg_bytes = sum(by for _, by in full) / len(full)
     # end to end from pinned host memory
-    for _ in range(2):
-        step(from_host=True)
-    ms_e2e = timed(args.steps, from_host=True)
+    timed_e2e(2)
+    ms_e2e = timed_e2e(args.steps)
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -272,6 +310,7 @@ def run_b200(args, rank, world):
                          "exceed the 126 MB L2 (no explicit flush)",
                    "prune": "reference algorithm on the host during setup, outside the timed region"},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "pipeline": "pinned host -> device copy of step i+1 overlaps the kernels of step i (2 buffers)",
                 "h2d_bytes_per_step": int(B * M * T * 4), "d2h_bytes_per_step": int(B * G * 4 + B * K * 8)},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "shift_stack_vec_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
