@@ -14,6 +14,7 @@ SYMBOLS = [
     "asw_srp_read_cc", "asw_srp_gcc_layout", "asw_srp_read_gcc",
     "asw_map_topk", "asw_shift_stack", "asw_shift_stack_norm",
     "asw_geometry_cluster",
+    "asw_peaks_create", "asw_peaks_destroy", "asw_peaks_find",
 ]
 
 
@@ -51,10 +52,9 @@ def load():
     lib.asw_shift_stack.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
     lib.asw_shift_stack_norm.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.asw_geometry_cluster.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
-    if hasattr(lib, "asw_peaks_create"):
-        lib.asw_peaks_create.argtypes = [c.POINTER(vp), i32, i32, i32, i32, i32, vp, vp]
-        lib.asw_peaks_destroy.argtypes = [vp]
-        lib.asw_peaks_find.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp]
+    lib.asw_peaks_create.argtypes = [c.POINTER(vp), i32, i32, i32, i32, i32, vp, vp, vp, c.c_double]
+    lib.asw_peaks_destroy.argtypes = [vp]
+    lib.asw_peaks_find.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name, None)
         if fn is not None and name not in ("asw_last_error", "asw_launch_count"):

@@ -119,6 +119,55 @@ class NativeSRP:
         return buf
 
 
+class NativePeaks:
+    """Device peak picking (asw_peaks_t): fill_powermap_torch + MAX_POWER + find_valid_peak_new
+    (sep/Traditional_SP/SRP_Prunning.py:347-357, :432, :500-544) for a batch of maps."""
+
+    def __init__(self, power_index, member_mask, dis_matrix, n_grids, thresholds, ratio=4.0, device=None,
+                 max_peaks=1024):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.AswError("no CUDA device: peak picking on the device needs one (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        idx = np.where(member_mask, power_index, -1).astype(np.int32)
+        idx = np.ascontiguousarray(idx)
+        dis = np.ascontiguousarray(dis_matrix, dtype=np.float64)
+        thr = np.ascontiguousarray(thresholds, dtype=np.float64)
+        self.G = int(n_grids)
+        self.max_peaks = int(max_peaks)
+        Lx, Ly, Lz = idx.shape
+        self._h = ctypes.c_void_p()
+        _lib.check(self.lib.asw_peaks_create(ctypes.byref(self._h), self.device.index or 0, Lx, Ly, Lz, self.G,
+                                             idx.ctypes.data, dis.ctypes.data, thr.ctypes.data,
+                                             ctypes.c_double(ratio)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.asw_peaks_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def find(self, srp_map):
+        """(B, G) float32 CUDA -> (peaks (B, max_peaks) int32 padded with -1, count (B,) int32, MAX_POWER (B,))."""
+        if srp_map.dim() == 1:
+            srp_map = srp_map.unsqueeze(0)
+        _require_cuda(srp_map, "srp_map", torch.float32)
+        B, G = srp_map.shape
+        if G != self.G:
+            raise _lib.AswError(f"map has {G} hypercubes, handle was built for {self.G}")
+        peaks = torch.empty((B, self.max_peaks), device=srp_map.device, dtype=torch.int32)
+        count = torch.empty((B,), device=srp_map.device, dtype=torch.int32)
+        mx = torch.empty((B,), device=srp_map.device, dtype=torch.float32)
+        _lib.check(self.lib.asw_peaks_find(self._h, _ptr(srp_map), B, _ptr(peaks), self.max_peaks, _ptr(count),
+                                           _ptr(mx), _stream(srp_map.device)))
+        return peaks, count, mx
+
+
 def map_topk(srp_map, K, idx_offset=0):
     """(B, G) float32 CUDA -> values (B, K) float32, indices (B, K) int32 (descending, ties to lower index)."""
     if srp_map.dim() == 1:

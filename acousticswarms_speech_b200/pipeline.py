@@ -71,6 +71,23 @@ class FrontEnd:
                 consumer(out, i, n)
         return launches
 
+    # ---- pruning ---------------------------------------------------------------------------------
+    def find_peaks(self, map_dev):
+        """Device peak picking for the whole batch -> per mixture (ids list, values array, MAX_POWER)."""
+        peaks, count, mx = self.node.native_peaks.find(map_dev)
+        vals = torch.gather(map_dev, 1, peaks.clamp(min=0).to(torch.int64))
+        peaks_h, count_h, mx_h, vals_h = peaks.cpu().numpy(), count.cpu().numpy(), mx.cpu().numpy(), vals.cpu().numpy()
+        out = []
+        for b in range(map_dev.shape[0]):
+            n = min(int(count_h[b]), peaks_h.shape[1])
+            out.append(([int(i) for i in peaks_h[b, :n]], vals_h[b, :n], float(mx_h[b])))
+        return out
+
+    def prune(self, map_dev):
+        """Apply_SRP_PHAT's pruning for every mixture of the batch: peaks on the device, the greedy
+        hypercube selection (SRP_Prunning.py:547-643) on the host -> list (per mixture) of list[Patch]."""
+        return [self.node.local_source_adaptive(ids, vals) for ids, vals, _ in self.find_peaks(map_dev)]
+
     # ---- host helpers ----------------------------------------------------------------------------
     def prune_host(self, srp_map_host):
         """The reference's pruning (SRP_Prunning.py:347-357, 500-643) on one mixture's map -> list[Patch]."""

@@ -148,7 +148,11 @@ class SRP_PHAT(object):
 
         # device handle: fractional pair lags replace mode_mat_flat_real/imag (:221-243)
         self.native = None
+        self.native_peaks = None
         if build_native:
+            self.native_peaks = native.NativePeaks(self.POWER_INDEX, self._member, self.dis_matrix,
+                                                   self.grids.shape[0], self.threshold, SRP_THRESHOLD_RATIO,
+                                                   device=self.device)
             lag = native.pair_lags(self.grids, self.mic_pos, FS, C)
             self.native = native.NativeSRP(lag, self.num_mic, device=self.device, bin0=int(self.freq_bins[0]),
                                            bin1=int(self.freq_bins[-1]) + 1, tol=PHAT_TOL, oversample=oversample)
@@ -295,7 +299,17 @@ class SRP_PHAT(object):
 
     # ---- pruning -----------------------------------------------------------------------------
     def find_valid_peak_new(self, rato=SRP_THRESHOLD_RATIO):
-        """:500-544."""
+        """:500-544.  On the device when this object owns a CUDA handle (the map is already there);
+        the numpy version below serves host-only geometry objects (``build_native=False``)."""
+        if self.native_peaks is not None and rato == SRP_THRESHOLD_RATIO and self.SRP_map.is_cuda:
+            peaks, count, _ = self.native_peaks.find(self.SRP_map.to(torch.float32))
+            n = int(count[0])
+            if n > self.native_peaks.max_peaks:
+                raise _lib.AswError(f"{n} peak clusters exceed the device list of {self.native_peaks.max_peaks}")
+            return [int(i) for i in peaks[0, :n].cpu().numpy()]
+        return self._find_valid_peak_host(rato)
+
+    def _find_valid_peak_host(self, rato=SRP_THRESHOLD_RATIO):
         thr = self.threshold[0] * self.MAX_POWER
         if thr < self.threshold[1]:
             thr = self.threshold[1]
@@ -322,14 +336,19 @@ class SRP_PHAT(object):
         _, first = np.unique(ids, return_index=True)
         return [int(i) for i in ids[np.sort(first)]]
 
-    def local_source_adaptive(self):
-        """:547-643 -> list[Patch]."""
-        peak_index = self.find_valid_peak_new()
-        m = self._map_host if hasattr(self, "_map_host") else self.SRP_map.cpu().numpy()
+    def local_source_adaptive(self, peak_index=None, peak_values=None):
+        """:547-643 -> list[Patch].  ``peak_index`` / ``peak_values`` may be supplied by the batched front
+        end (device peak picking for many mixtures at once); by default they come from this object's map."""
+        if peak_index is None:
+            peak_index = self.find_valid_peak_new()
         if len(peak_index) == 0:
             self.peak_candidate = np.zeros((0, 3))
             return []
-        peaks = m[peak_index]
+        if peak_values is None:
+            m = self._map_host if hasattr(self, "_map_host") else self.SRP_map.cpu().numpy()
+            peaks = m[peak_index]
+        else:
+            peaks = np.asarray(peak_values)
         peaks_pos = self.grids[peak_index]
         self.peaks, self.peaks_pos = peaks, peaks_pos
         peaks_sample = np.array([self.clusters[i].sample_offset for i in peak_index])

@@ -128,6 +128,28 @@ int asw_shift_stack_norm(const float* mix_dev, const int32_t* shifts_dev, const 
                          double* work_dev, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Peak picking on the device: fill_powermap_torch + MAX_POWER + find_valid_peak_new
+ * (sep/Traditional_SP/SRP_Prunning.py:347-357, :432, :500-544) for a batch of maps.
+ *   power_index [Lx][Ly][Lz] int32  cluster id of every 5 cm voxel, -1 where the voxel belongs to no
+ *                                   cluster (keep-out box); the reference's POWER_INDEX with its
+ *                                   zero-initialised non-members marked
+ *   dis_matrix  [Lx][Ly] float64    SRP_Prunning.py:140-144
+ *   threshold3  {ratio, floor, ceiling} (sep/Mic_Array.py:120), ratio2 = 4 (:500)
+ * asw_peaks_find:
+ *   map_dev       [B][G] float32
+ *   peaks_dev     [B][max_peaks] int32 out: cluster ids in the reference's order (first occurrence in
+ *                 C order over the interior voxels), padded with -1
+ *   count_dev     [B] int32 out: number of peak clusters (may exceed max_peaks / 2048: list truncated)
+ *   max_power_dev [B] float32 out: MAX_POWER
+ * Comparisons are evaluated in double on the float32 map values, exactly as the host code does. */
+typedef struct asw_peaks asw_peaks_t;
+int asw_peaks_create(asw_peaks_t** out, int device, int Lx, int Ly, int Lz, int G, const int32_t* power_index,
+                     const double* dis_matrix, const double* threshold3, double ratio2);
+int asw_peaks_destroy(asw_peaks_t* h);
+int asw_peaks_find(asw_peaks_t* h, const float* map_dev, int B, int32_t* peaks_dev, int max_peaks,
+                   int32_t* count_dev, float* max_power_dev, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Host-side hypercube table build: SRP_PHAT.Map_3D_TDoA + search_cluster
  * (sep/Traditional_SP/SRP_Prunning.py:277-344).  Pure CPU code (no device needed).
  *   offsets [Lx][Ly][Lz][D] int64  quantised TDoA vector of every voxel (:327-331)

@@ -154,3 +154,33 @@ def test_full_size_properties(cuda_device, desk):
     best = ma.SRP_node.clusters[int(m.argmax())].sample_offset
     assert np.abs(best - true).max() <= 4.0, (best, true)
     assert m.max() > 0.5            # a single coherent source scores near 1
+
+
+def test_device_peak_picking_equals_host(cuda_device, desk):
+    """asw_peaks_find vs the oracle's find_valid_peaks on the SAME float32 maps: identical id lists
+    (both compare in double; integer output: bit-exact, order included)."""
+    g, scene, mix, ma = desk
+    node = ma.SRP_node
+    from acousticswarms_speech_b200.pipeline import FrontEnd
+    fe = FrontEnd(node)
+    mixes = np.stack([mix, synth.mixture(scene, 5, mix.shape[1], seed=21), synth.mixture(scene, 1, mix.shape[1], seed=22),
+                      np.zeros_like(mix)])
+    smap, _, _ = fe.score(torch.from_numpy(mixes).cuda())
+    res = fe.find_peaks(smap)
+    maps = smap.cpu().numpy()
+    clusters = [(None, None, c.index) for c in node.clusters]
+    for b in range(mixes.shape[0]):
+        m = maps[b].astype(np.float64)
+        pm, pi = prune_oracle.fill_powermap(m, clusters, (node.Lx, node.Ly, node.Lz))
+        want = prune_oracle.find_valid_peaks(pm, pi, node.dis_matrix, float(m.max()), len(clusters))
+        ids, vals, mx = res[b]
+        assert ids == want
+        assert mx == maps[b].max()
+        assert np.array_equal(vals, maps[b][want]) if want else len(vals) == 0
+    # and the patches built from device peaks equal the host path's
+    patches = fe.prune(smap)
+    host = fe.prune_host(maps[0])
+    assert len(patches[0]) == len(host)
+    for a, h in zip(patches[0], host):
+        assert np.array_equal(a.sample_offset, h.sample_offset) and np.array_equal(a.width_list, h.width_list)
+    assert patches[3] == []          # silence: no peaks
