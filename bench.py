@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="mixtures per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused-norm", action="store_true", help="shift-stack fused with normalize_input")
+    ap.add_argument("--streams", type=int, default=2, choices=[1, 2],
+                    help="2: scoring (SM/shared-memory bound) of step i+1 overlaps the shift-stack (HBM bound) of step i")
     return ap.parse_args()
 
 
@@ -204,19 +206,37 @@ def run_b200(args, rank, world):
     gather_val = [torch.empty((B, K), device=dev) for _ in range(world)] if world > 1 else None
     gather_idx = [torch.empty((B, K), device=dev, dtype=torch.int32) for _ in range(world)] if world > 1 else None
 
+    stack_stream = torch.cuda.Stream(device=dev) if args.streams == 2 else None
+
     def compute(src, events=None, to_host=False):
+        nonlocal stack_stream
+        """One step.  With two streams the scoring half runs on the current stream and the shift-stack
+        half on `stack_stream` behind an event, so consecutive steps software-pipeline."""
         m, val, idx = fe.score(src)
         if world > 1:          # the one collective of the path: every rank learns every mixture's top-K
             dist.all_gather(gather_val, val)
             dist.all_gather(gather_idx, idx)
         peaks, count, _ = node.native_peaks.find(m)       # fill_powermap + find_valid_peak_new on the device
-        fe.stack(src, shifts_dev, mi_dev, fused_norm=args.fused_norm, events=events)
         if to_host:
             peaks_pin.copy_(peaks, non_blocking=True)
             count_pin.copy_(count, non_blocking=True)
             map_pin.copy_(m, non_blocking=True)
             val_pin.copy_(val, non_blocking=True)
             idx_pin.copy_(idx, non_blocking=True)
+        if stack_stream is None:
+            fe.stack(src, shifts_dev, mi_dev, fused_norm=args.fused_norm, events=events)
+        else:
+            main = torch.cuda.current_stream(dev)
+            scored = torch.cuda.Event()
+            scored.record(main)
+            stack_stream.wait_event(scored)      # the patch list of a step depends on its own scores
+            with torch.cuda.stream(stack_stream):
+                fe.stack(src, shifts_dev, mi_dev, fused_norm=args.fused_norm, events=events)
+
+    def join_streams():
+        nonlocal stack_stream
+        if stack_stream is not None:
+            torch.cuda.current_stream(dev).wait_stream(stack_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -238,6 +258,7 @@ def run_b200(args, rank, world):
         e0.record()
         for _ in range(n_steps):
             compute(mix_dev, events=events)
+        join_streams()
         e1.record()
         barrier()
         return reduce_max_ms(e0.elapsed_time(e1))
@@ -268,7 +289,11 @@ def run_b200(args, rank, world):
                     copied[nxt].record()
             main.wait_event(copied[cur])
             compute(in_bufs[cur], to_host=True)
-            consumed[cur].record()
+            if stack_stream is not None:
+                consumed[cur].record(stack_stream)     # the shift-stack is the last reader of the input buffer
+            else:
+                consumed[cur].record()
+        join_streams()
         e1.record()
         barrier()
         return reduce_max_ms(e0.elapsed_time(e1))
@@ -282,9 +307,12 @@ def run_b200(args, rank, world):
     l0 = _lib.launch_count()
     ms = timed(args.steps)
     launches = _lib.launch_count() - l0
-    # kernel-level timing of the dominant kernel (shift-stack) with events on the launching stream
+    # kernel-level timing of the dominant kernel (shift-stack) with events on the launching stream; this
+    # pass runs single-stream so the kernel is timed alone, not while sharing SMs with the scoring kernels
     events = []
+    saved_stream, stack_stream = stack_stream, None
     timed(max(2, min(args.steps, 5)), events=events)
+    stack_stream = saved_stream
     torch.cuda.synchronize()
     k_ms = [a.elapsed_time(b) for a, b, _ in events]
     k_bytes = [4.0 * n * M * T for _, _, n in events]
@@ -311,7 +339,7 @@ def run_b200(args, rank, world):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "mixtures_per_gpu_per_step": B, "hypercubes": G, "mics": M, "speakers": N_SPK,
                    "samples": T, "fs": FS, "coarse_patches_per_step_per_gpu": N, "net_batch": fe.net_batch,
-                   "fused_norm": bool(args.fused_norm), "parallelism": f"mixtures sharded over {world} GPU(s)",
+                   "fused_norm": bool(args.fused_norm), "streams": args.streams, "parallelism": f"mixtures sharded over {world} GPU(s)",
                    "l2": f"inputs {B * M * T * 4 / 1e6:.0f} MB + stacked output {N * M * T * 4 / 1e9:.2f} GB per step "
                          "exceed the 126 MB L2 (no explicit flush)",
                    "prune": "peak picking (fill_powermap + find_valid_peak_new) on the device inside the step; the "
