@@ -184,3 +184,29 @@ def test_device_peak_picking_equals_host(cuda_device, desk):
     for a, h in zip(patches[0], host):
         assert np.array_equal(a.sample_offset, h.sample_offset) and np.array_equal(a.width_list, h.width_list)
     assert patches[3] == []          # silence: no peaks
+
+
+def test_c5_stress_subset_parity(cuda_device):
+    """Config C5 scale (16 mics, 10 s, dense grid, G ~ 1e5, P = 120, 25 windows): the generic STFT path,
+    multi-group / multi-chunk table staging.  The oracle evaluates the reference contraction on a random
+    subset of hypercubes (the full (G, F, P) table would be ~90 GB)."""
+    from acousticswarms_speech_b200.srp_phat import SRP_PHAT
+    rng = np.random.default_rng(16)
+    scene = synth.table_array(16, rng)
+    node = SRP_PHAT(scene.mic_positions, constants.freq_bins, scene.roi, FS=48000, n_fft=constants.n_fft,
+                    grid_size=0.025, grid_size_z=0.05, threshold=list(constants.SRP_THRESHOLDS), WIDTH=8)
+    G = node.grids.shape[0]
+    assert G > 30000
+    T = 480000
+    mix = synth.mixture(scene, 4, T, seed=8)
+    got = node.native.score(torch.from_numpy(mix).cuda(), 36000)[0].cpu().numpy()
+    assert got.shape == (G,) and (got >= 0).all() and got.max() > 0.05
+    sel = np.sort(rng.choice(G, 300, replace=False))
+    # oracle: same staged arithmetic, contraction only on the selected hypercubes
+    want = np.zeros(len(sel))
+    for s0 in srp_oracle.window_starts(T, 36000):
+        X = srp_oracle.stft_window(mix[:, s0:s0 + 36000], 2048, 512)
+        CC = srp_oracle.cross_spectra(srp_oracle.phat(X), constants.freq_bins)
+        want = np.maximum(want, srp_oracle.contract(CC, node.grids[sel], scene.mic_positions, constants.freq_bins,
+                                                    48000, 2048))
+    assert np.abs(got[sel] - want).max() <= TOL * got.max()
