@@ -203,8 +203,11 @@ def run_b200(args, rank, world):
     MAXP = node.native_peaks.max_peaks
     peaks_pin = torch.empty((B, MAXP), dtype=torch.int32).pin_memory()
     count_pin = torch.empty((B,), dtype=torch.int32).pin_memory()
-    gather_val = [torch.empty((B, K), device=dev) for _ in range(world)] if world > 1 else None
-    gather_idx = [torch.empty((B, K), device=dev, dtype=torch.int32) for _ in range(world)] if world > 1 else None
+    # the one collective: all ranks' (value, index) top-K lists, packed into a single all-gather per step
+    # and issued on a side stream so it overlaps the shift-stack
+    pack = torch.empty((B, 2 * K), device=dev) if world > 1 else None
+    gathered = torch.empty((world * B, 2 * K), device=dev) if world > 1 else None
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
 
     stack_stream = torch.cuda.Stream(device=dev) if args.streams == 2 else None
 
@@ -214,8 +217,14 @@ def run_b200(args, rank, world):
         half on `stack_stream` behind an event, so consecutive steps software-pipeline."""
         m, val, idx = fe.score(src)
         if world > 1:          # the one collective of the path: every rank learns every mixture's top-K
-            dist.all_gather(gather_val, val)
-            dist.all_gather(gather_idx, idx)
+            torch.cuda.current_stream(dev).wait_stream(comm_stream)   # previous step's gather has read `pack`
+            pack[:, :K] = val
+            pack[:, K:] = idx.view(torch.float32)
+            packed = torch.cuda.Event()
+            packed.record()
+            comm_stream.wait_event(packed)
+            with torch.cuda.stream(comm_stream):
+                dist.all_gather_into_tensor(gathered, pack)
         peaks, count, _ = node.native_peaks.find(m)       # fill_powermap + find_valid_peak_new on the device
         if to_host:
             peaks_pin.copy_(peaks, non_blocking=True)
@@ -237,6 +246,8 @@ def run_b200(args, rank, world):
         nonlocal stack_stream
         if stack_stream is not None:
             torch.cuda.current_stream(dev).wait_stream(stack_stream)
+        if comm_stream is not None:
+            torch.cuda.current_stream(dev).wait_stream(comm_stream)
 
     def barrier():
         torch.cuda.synchronize()
