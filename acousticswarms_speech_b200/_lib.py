@@ -15,6 +15,8 @@ SYMBOLS = [
     "asw_map_topk", "asw_shift_stack", "asw_shift_stack_norm",
     "asw_geometry_cluster",
     "asw_peaks_create", "asw_peaks_destroy", "asw_peaks_find",
+    "asw_select_create", "asw_select_destroy", "asw_select_patches",
+    "asw_build_shift_table", "asw_shift_stack_counted",
 ]
 
 
@@ -55,6 +57,12 @@ def load():
     lib.asw_peaks_create.argtypes = [c.POINTER(vp), i32, i32, i32, i32, i32, vp, vp, vp, c.c_double]
     lib.asw_peaks_destroy.argtypes = [vp]
     lib.asw_peaks_find.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp]
+    lib.asw_select_create.argtypes = [c.POINTER(vp), i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp,
+                                      i32, i32, i32]
+    lib.asw_select_destroy.argtypes = [vp]
+    lib.asw_select_patches.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp, vp, vp, i32, vp]
+    lib.asw_build_shift_table.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp]
+    lib.asw_shift_stack_counted.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name, None)
         if fn is not None and name not in ("asw_last_error", "asw_launch_count"):

@@ -450,6 +450,18 @@ int asw_shift_stack(const float* mix_dev, const int32_t* shifts_dev, const int32
     return launch_shift_stack(mix_dev, shifts_dev, mix_index_dev, N, B, M, T, out_dev, (cudaStream_t)stream);
 }
 
+int asw_shift_stack_counted(const float* mix_dev, const int32_t* shifts_dev, const int32_t* mix_index_dev,
+                            const int32_t* n_valid_dev, int n_base, int N, int B, int M, int T, float* out_dev,
+                            void* stream) {
+    if (!mix_dev || !shifts_dev || !mix_index_dev || !n_valid_dev || !out_dev || N < 0 || n_base < 0 || B < 1 || M < 1 ||
+        M > kMaxMics || T < 1) {
+        set_error("asw_shift_stack_counted: null buffer or bad shape (N=%d B=%d M=%d T=%d)", N, B, M, T);
+        return ASW_ERR_ARG;
+    }
+    return launch_shift_stack_counted(mix_dev, shifts_dev, mix_index_dev, n_valid_dev, n_base, N, B, M, T, out_dev,
+                                      (cudaStream_t)stream);
+}
+
 int asw_shift_stack_norm(const float* mix_dev, const int32_t* shifts_dev, const int32_t* mix_index_dev, int N, int B,
                          int M, int T, float* out_dev, float* means_dev, float* stds_dev, double* work_dev,
                          void* stream) {

@@ -79,8 +79,10 @@ __global__ void __launch_bounds__(kThreads) shift_stack_vec_kernel(const float* 
                                                                     const int32_t* __restrict__ mix_index, int M, int T,
                                                                     float* __restrict__ out,
                                                                     const double* __restrict__ work,
-                                                                    float* __restrict__ means, float* __restrict__ stds) {
+                                                                    float* __restrict__ means, float* __restrict__ stds,
+                                                                    const int32_t* __restrict__ n_valid, int n_base) {
     const int c = blockIdx.y, n = blockIdx.z;
+    if (n_valid && n_base + n >= *n_valid) return;
     const int row = n * M + c;
     const int mi = mix_index ? mix_index[n] : 0;
     const float* src = mix + ((size_t)mi * M + c) * (size_t)T;
@@ -114,8 +116,10 @@ __global__ void __launch_bounds__(kThreads) shift_stack_scalar_kernel(const floa
                                                                        int T, float* __restrict__ out,
                                                                        const double* __restrict__ work,
                                                                        float* __restrict__ means,
-                                                                       float* __restrict__ stds) {
+                                                                       float* __restrict__ stds,
+                                                                       const int32_t* __restrict__ n_valid, int n_base) {
     const int c = blockIdx.y, n = blockIdx.z;
+    if (n_valid && n_base + n >= *n_valid) return;
     const int row = n * M + c;
     const int mi = mix_index ? mix_index[n] : 0;
     const float* src = mix + ((size_t)mi * M + c) * (size_t)T;
@@ -194,7 +198,8 @@ __global__ void __launch_bounds__(kThreads) shift_ref_stats_kernel(const float* 
 
 template <bool NORM>
 int launch_rows(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int M, int T, float* out,
-                const double* work, float* means, float* stds, cudaStream_t s) {
+                const double* work, float* means, float* stds, cudaStream_t s, const int32_t* n_valid = nullptr,
+                int n_base = 0) {
     const bool vec = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(mix) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const int per_cta = kThreads * kVpt * 4;  // samples per CTA
@@ -208,10 +213,11 @@ int launch_rows(const float* mix, const int32_t* shifts, const int32_t* mix_inde
         float* mu = means ? means + n0 : nullptr;
         float* sd = stds ? stds + n0 : nullptr;
         if (vec) {
-            shift_stack_vec_kernel<NORM><<<grid, kThreads, 0, s>>>(mix, sh, mi, M, T, o, wk, mu, sd);
+            shift_stack_vec_kernel<NORM><<<grid, kThreads, 0, s>>>(mix, sh, mi, M, T, o, wk, mu, sd, n_valid, n_base + n0);
             ASW_LAUNCH_CHECK("shift_stack_vec_kernel");
         } else {
-            shift_stack_scalar_kernel<NORM><<<grid, kThreads, 0, s>>>(mix, sh, mi, M, T, o, wk, mu, sd);
+            shift_stack_scalar_kernel<NORM><<<grid, kThreads, 0, s>>>(mix, sh, mi, M, T, o, wk, mu, sd, n_valid,
+                                                                      n_base + n0);
             ASW_LAUNCH_CHECK("shift_stack_scalar_kernel");
         }
     }
@@ -225,6 +231,14 @@ int launch_shift_stack(const float* mix, const int32_t* shifts, const int32_t* m
     (void)B;
     if (N == 0) return ASW_OK;
     return launch_rows<false>(mix, shifts, mix_index, N, M, T, out, nullptr, nullptr, nullptr, s);
+}
+
+int launch_shift_stack_counted(const float* mix, const int32_t* shifts, const int32_t* mix_index, const int32_t* n_valid,
+                               int n_base, int N, int B, int M, int T, float* out, cudaStream_t s) {
+    (void)B;
+    if (N == 0) return ASW_OK;
+    return launch_rows<false>(mix, shifts + (size_t)n_base * M, mix_index + n_base, N, M, T, out, nullptr, nullptr,
+                              nullptr, s, n_valid, n_base);
 }
 
 int launch_shift_stack_norm(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int B, int M,

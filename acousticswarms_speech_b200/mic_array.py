@@ -81,7 +81,10 @@ class Mic_Array(object):
         self.original_times = 0
         WIN_SIZE = window_length(mix_data.shape[1])
         self.SRP_node.SRP_Map_WINDOW_new(mix_data, window=WIN_SIZE)
-        patch_list = self.SRP_node.local_source_adaptive()
+        if self.SRP_node.native is not None:
+            patch_list = self.SRP_node.local_source_adaptive_device()
+        else:
+            patch_list = self.SRP_node.local_source_adaptive()
         return patch_list, np.zeros((3, 3))
 
     def Spotform_Big_Patch(self, mix_data, patch_list, spot_model):

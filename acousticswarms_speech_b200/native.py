@@ -168,6 +168,106 @@ class NativePeaks:
         return peaks, count, mx
 
 
+class NativeSelect:
+    """Device greedy selection of coarse patches (asw_select_t): SRP_PHAT.local_source_adaptive
+    (sep/Traditional_SP/SRP_Prunning.py:547-643) for a batch of mixtures."""
+
+    def __init__(self, cluster_offsets, Offset_5, Offset_1, Range_spk, Axis_range, width, device=None,
+                 max_patches=64):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.AswError("no CUDA device: patch selection on the device needs one (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        cl = np.ascontiguousarray(cluster_offsets, dtype=np.int32)
+        self.G, self.D = cl.shape
+        Ny5, Nx5, Nz, D = Offset_5.shape
+        Ny1, Nx1, Nz1, _ = Offset_1.shape
+        assert Nz1 == Nz and D == self.D
+        o5 = Offset_5.reshape(-1, D)
+        order = np.argsort(o5[:, 0], kind="stable")
+        iy, ix, iz = np.unravel_index(np.arange(o5.shape[0]), (Ny5, Nx5, Nz))
+        ok = (5 * iy < Ny1) & (5 * ix < Nx1)
+        o1 = np.full(o5.shape, np.nan)
+        o1[ok] = Offset_1[5 * iy[ok], 5 * ix[ok], iz[ok]]
+        off5_sorted = np.ascontiguousarray(o5[order].T)
+        off1_at5 = np.ascontiguousarray(o1[order].T)
+        vox5 = np.ascontiguousarray((iy * Nx5 + ix)[order].astype(np.int32))
+        r = Range_spk
+        xx5 = np.ascontiguousarray(np.arange(r[0], r[1], 0.05))
+        yy5 = np.ascontiguousarray(np.arange(r[2], r[3], 0.05))
+        assert xx5.shape[0] == Nx5 and yy5.shape[0] == Ny5
+        axis = np.array([Axis_range[0][0], Axis_range[0][1], Axis_range[1][0], Axis_range[1][1]], dtype=np.float64)
+        off1 = np.ascontiguousarray(Offset_1, dtype=np.float64)
+        self.max_patches = int(max_patches)
+        self._h = ctypes.c_void_p()
+        _lib.check(self.lib.asw_select_create(ctypes.byref(self._h), self.device.index or 0, self.G, self.D, int(width),
+                                              cl.ctypes.data, off5_sorted.ctypes.data, off1_at5.ctypes.data,
+                                              vox5.ctypes.data, o5.shape[0], Nx5, Ny5, xx5.ctypes.data,
+                                              yy5.ctypes.data, axis.ctypes.data, off1.ctypes.data, Ny1, Nx1, Nz))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.asw_select_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def select(self, srp_map, peaks, count):
+        """-> (n_patches (B,), offsets (B, max_patches, D), widths (B, max_patches), peak ids (B, max_patches)), int32 CUDA."""
+        _require_cuda(srp_map, "srp_map", torch.float32)
+        _require_cuda(peaks, "peaks", torch.int32)
+        _require_cuda(count, "count", torch.int32)
+        B = srp_map.shape[0]
+        dev = srp_map.device
+        n = torch.empty((B,), device=dev, dtype=torch.int32)
+        off = torch.zeros((B, self.max_patches, self.D), device=dev, dtype=torch.int32)
+        wid = torch.zeros((B, self.max_patches), device=dev, dtype=torch.int32)
+        pk = torch.full((B, self.max_patches), -1, device=dev, dtype=torch.int32)
+        _lib.check(self.lib.asw_select_patches(self._h, _ptr(srp_map), _ptr(peaks), peaks.shape[1], _ptr(count), B,
+                                               _ptr(n), _ptr(off), _ptr(wid), _ptr(pk), self.max_patches,
+                                               _stream(dev)))
+        return n, off, wid, pk
+
+
+def build_shift_table(n_patches, offsets, capacity, shifts=None, mix_index=None, n_total=None):
+    """Per-mixture patch lists -> dense (capacity, D + 1) int32 shift table, (capacity,) mixture index and the
+    device-resident total, without leaving the device."""
+    _require_cuda(n_patches, "n_patches", torch.int32)
+    _require_cuda(offsets, "offsets", torch.int32)
+    B, max_patches, D = offsets.shape
+    dev = offsets.device
+    if shifts is None:
+        shifts = torch.zeros((capacity, D + 1), device=dev, dtype=torch.int32)
+    if mix_index is None:
+        mix_index = torch.zeros((capacity,), device=dev, dtype=torch.int32)
+    if n_total is None:
+        n_total = torch.zeros((1,), device=dev, dtype=torch.int32)
+    _lib.check(_lib.load().asw_build_shift_table(_ptr(n_patches), _ptr(offsets), B, max_patches, D, _ptr(shifts),
+                                                 _ptr(mix_index), _ptr(n_total), int(capacity), _stream(dev)))
+    return shifts, mix_index, n_total
+
+
+def shift_stack_counted(mix, shifts, mix_index, n_total, n_base, N, out):
+    """shift_stack for rows [n_base, n_base + N) of a device-built table; rows >= n_total[0] are skipped."""
+    if mix.dim() == 2:
+        mix = mix.unsqueeze(0)
+    _require_cuda(mix, "mix", torch.float32)
+    _require_cuda(shifts, "shifts", torch.int32)
+    _require_cuda(mix_index, "mix_index", torch.int32)
+    _require_cuda(n_total, "n_total", torch.int32)
+    _require_cuda(out, "out", torch.float32)
+    B, M, T = mix.shape
+    if shifts.shape[1] != M or out.numel() < N * M * T:
+        raise _lib.AswError("shift table / output shape mismatch")
+    _lib.check(_lib.load().asw_shift_stack_counted(_ptr(mix), _ptr(shifts), _ptr(mix_index), _ptr(n_total), int(n_base),
+                                                   int(N), B, M, T, _ptr(out), _stream(mix.device)))
+    return out
+
+
 def map_topk(srp_map, K, idx_offset=0):
     """(B, G) float32 CUDA -> values (B, K) float32, indices (B, K) int32 (descending, ties to lower index)."""
     if srp_map.dim() == 1:

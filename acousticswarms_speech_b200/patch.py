@@ -7,12 +7,27 @@ import numpy as np
 
 
 class Patch(object):
-    def __init__(self, sample_offset, width_list, area_points, peak_pos=None):
+    def __init__(self, sample_offset, width_list, area_points, peak_pos=None, area_fn=None):
         self.sample_offset = sample_offset          # int64 (M-1,): hypercube centre, samples vs mic 0
         self.width_list = np.copy(width_list)       # full width per dimension (8 coarse, 4 fine, 2 centre)
-        self.area_points = area_points              # (3, n) 1 cm voxels inside, or None
+        self._area_points = area_points             # (3, n) 1 cm voxels inside, or None
+        self._area_fn = area_fn                     # builds area_points on first use (device-selected patches)
         self.num_pair = sample_offset.shape[0]
         self.peak_pos = peak_pos
+
+    @property
+    def area_points(self):
+        """(3, n) 1 cm voxels whose TDoA vector lies in the hypercube.  Patches selected on the device
+        carry a builder instead of the points (SRP_Prunning.py:41-61 evaluated on first use)."""
+        if self._area_points is None and self._area_fn is not None:
+            self._area_points = self._area_fn()
+            self._area_fn = None
+        return self._area_points
+
+    @area_points.setter
+    def area_points(self, value):
+        self._area_points = value
+        self._area_fn = None
 
     def area_size(self):
         if self.area_points is None or self.area_points.shape[1] == 0:

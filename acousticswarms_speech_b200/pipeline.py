@@ -84,9 +84,43 @@ class FrontEnd:
         return out
 
     def prune(self, map_dev):
-        """Apply_SRP_PHAT's pruning for every mixture of the batch: peaks on the device, the greedy
-        hypercube selection (SRP_Prunning.py:547-643) on the host -> list (per mixture) of list[Patch]."""
+        """Apply_SRP_PHAT's pruning for every mixture of the batch, on the device (peak picking + greedy
+        hypercube selection, SRP_Prunning.py:500-643) -> list (per mixture) of list[Patch]."""
+        n, off, wid, pk = self.select(map_dev)
+        n_h, off_h, wid_h, pk_h = n.cpu().numpy(), off.cpu().numpy(), wid.cpu().numpy(), pk.cpu().numpy()
+        return [self.node.patches_from_device(min(int(n_h[b]), off_h.shape[1]), off_h[b], wid_h[b], pk_h[b])
+                for b in range(map_dev.shape[0])]
+
+    def prune_host_greedy(self, map_dev):
+        """Same with the greedy selection on the host (device peaks): the cross-check of `prune`."""
         return [self.node.local_source_adaptive(ids, vals) for ids, vals, _ in self.find_peaks(map_dev)]
+
+    def select(self, map_dev):
+        """Device peak picking + greedy selection -> (n (B,), offsets (B, P, D), widths (B, P), peak ids (B, P))."""
+        peaks, count, _ = self.node.native_peaks.find(map_dev)
+        return self.node.native_select.select(map_dev, peaks, count)
+
+    def shift_table(self, n, offsets, capacity):
+        """Dense device shift table of all selected patches of the batch (no host round trip)."""
+        return native.build_shift_table(n, offsets, capacity)
+
+    def stack_counted(self, mix_dev, shifts, mix_index, n_total, capacity, consumer=None, events=None):
+        """`stack` driven by a device-resident patch count: launches ceil(capacity / net_batch) batches,
+        rows beyond n_total are skipped on the device."""
+        B, M, T = mix_dev.shape
+        bufs = self._ring(M, T)
+        for k, i in enumerate(range(0, capacity, self.net_batch)):
+            n = min(self.net_batch, capacity - i)
+            buf = bufs[k % self.ring]
+            if events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            native.shift_stack_counted(mix_dev, shifts, mix_index, n_total, i, n, buf)
+            if events is not None:
+                e1.record()
+                events.append((e0, e1, n))
+            if consumer is not None:
+                consumer(buf, i, n)
 
     # ---- host helpers ----------------------------------------------------------------------------
     def prune_host(self, srp_map_host):

@@ -149,6 +149,7 @@ class SRP_PHAT(object):
         # device handle: fractional pair lags replace mode_mat_flat_real/imag (:221-243)
         self.native = None
         self.native_peaks = None
+        self._native_select = None
         if build_native:
             self.native_peaks = native.NativePeaks(self.POWER_INDEX, self._member, self.dis_matrix,
                                                    self.grids.shape[0], self.threshold, SRP_THRESHOLD_RATIO,
@@ -335,6 +336,41 @@ class SRP_PHAT(object):
         ids = self.POWER_INDEX[vox[:, 0] + 2, vox[:, 1] + 2, vox[:, 2] + 1]
         _, first = np.unique(ids, return_index=True)
         return [int(i) for i in ids[np.sort(first)]]
+
+    @property
+    def native_select(self):
+        """Device handle of the greedy selection; built on first use (it uploads the 1 cm TDoA volume)."""
+        if self._native_select is None and self.native is not None:
+            self._native_select = native.NativeSelect(
+                np.array([c.sample_offset for c in self.clusters], dtype=np.int32), self.Offset_5, self.Offset_1,
+                self.Range_spk, self.Axis_range, self.WIDTH, device=self.device)
+        return self._native_select
+
+    def _area_builder(self, centres, width):
+        return lambda: hyperbola_area_init(self.Axis_range, centres, width, self.Pos_5, self.Offset_5, self.Pos_1,
+                                           self.Offset_1, self._first5(), self._first1())
+
+    def patches_from_device(self, n, offsets, widths, peak_ids):
+        """Patch objects for one mixture from asw_select_patches' outputs (host arrays); ``area_points`` is
+        built on first access by the same code path the host selection uses."""
+        out = []
+        D = self.num_mic - 1
+        for q in range(int(n)):
+            centres = offsets[q].astype(np.int64)
+            w = np.full(D, int(widths[q]), dtype=np.int64)
+            out.append(Patch(centres, w, None, self.grids[int(peak_ids[q])],
+                             area_fn=self._area_builder(centres, int(widths[q]) + ERR_TOLERANCE)))
+        return out
+
+    def local_source_adaptive_device(self):
+        """:547-643 entirely on the device for this object's current map -> list[Patch]."""
+        m = self.SRP_map.to(torch.float32).unsqueeze(0).contiguous()
+        peaks, count, _ = self.native_peaks.find(m)
+        n, off, wid, pk = self.native_select.select(m, peaks, count)
+        n_h = int(n[0])
+        if n_h > self.native_select.max_patches:
+            raise _lib.AswError(f"{n_h} patches exceed the device list of {self.native_select.max_patches}")
+        return self.patches_from_device(n_h, off[0].cpu().numpy(), wid[0].cpu().numpy(), pk[0].cpu().numpy())
 
     def local_source_adaptive(self, peak_index=None, peak_values=None):
         """:547-643 -> list[Patch].  ``peak_index`` / ``peak_values`` may be supplied by the batched front

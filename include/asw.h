@@ -150,6 +150,49 @@ int asw_peaks_find(asw_peaks_t* h, const float* map_dev, int B, int32_t* peaks_d
                    int32_t* count_dev, float* max_power_dev, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Greedy selection of the coarse hypercube patches on the device: SRP_PHAT.local_source_adaptive
+ * (sep/Traditional_SP/SRP_Prunning.py:547-643, helpers :19-61) for a batch of mixtures, fed by
+ * asw_peaks_find.  Decisions (trimming, covered peaks, "is any 1 cm voxel inside") are evaluated in
+ * double on the same float64 volumes the reference builds in SRP_PHAT.__init__ (:148-170).
+ *   cluster_offsets [G][D] int32    quantised TDoA vector of every cluster (Grid_cluster.sample_offset)
+ *   off5_sorted     [D][n5] float64 Offset_5 flattened in C order ([y][x][z]), voxels sorted by
+ *                                   coordinate 0, stored coordinate-major
+ *   off1_at5        [D][n5] float64 Offset_1 at the 1 cm voxel (5*iy, 5*ix, iz) coinciding with each of
+ *                                   those 5 cm voxels, same order (NaN where it does not exist)
+ *   vox5            [n5] int32      iy * Nx5 + ix of the sorted voxels
+ *   xx5, yy5        float64         the 5 cm grid coordinates (np.arange, :149-150)
+ *   axis_range4     {x0, x1, y0, y1} (Axis_range, :146)
+ *   off1            [Ny1][Nx1][Nz][D] float64  Offset_1 (:167-170)
+ * asw_select_patches outputs, per mixture b (patch q < min(out_count[b], max_patches)):
+ *   out_offsets [B][max_patches][D] int32  Patch.sample_offset
+ *   out_width   [B][max_patches]    int32  Patch.width_list (identical in every dimension)
+ *   out_peak    [B][max_patches]    int32  cluster id whose centre is Patch.peak_pos
+ * Patch.area_points is not produced (the host builds it on demand for the patches that get subdivided). */
+typedef struct asw_select asw_select_t;
+int asw_select_create(asw_select_t** out, int device, int G, int D, int W, const int32_t* cluster_offsets,
+                      const double* off5_sorted, const double* off1_at5, const int32_t* vox5, int n5, int Nx5,
+                      int Ny5, const double* xx5, const double* yy5, const double* axis_range4,
+                      const double* off1, int Ny1, int Nx1, int Nz);
+int asw_select_destroy(asw_select_t* h);
+int asw_select_patches(asw_select_t* h, const float* map_dev, const int32_t* peaks_dev, int max_peaks,
+                       const int32_t* count_dev, int B, int32_t* out_count_dev, int32_t* out_offsets_dev,
+                       int32_t* out_width_dev, int32_t* out_peak_dev, int max_patches, void* stream);
+
+/* Dense shift table for asw_shift_stack from the per-mixture patch lists above:
+ *   shifts_dev [capacity][D+1] int32 (column 0 = 0), mix_index_dev [capacity] int32,
+ *   n_total_dev [1] int32 = min(total patches, capacity).  B <= 1024. */
+int asw_build_shift_table(const int32_t* count_dev, const int32_t* offsets_dev, int B, int max_patches, int D,
+                          int32_t* shifts_dev, int32_t* mix_index_dev, int32_t* n_total_dev, int capacity,
+                          void* stream);
+
+/* asw_shift_stack for patches [n_base, n_base + N) of a device-built table whose length lives on the
+ * device: patches at or beyond *n_valid_dev are skipped (no host synchronisation needed between the
+ * selection and the stacking).  out_dev receives N slots. */
+int asw_shift_stack_counted(const float* mix_dev, const int32_t* shifts_dev, const int32_t* mix_index_dev,
+                            const int32_t* n_valid_dev, int n_base, int N, int B, int M, int T, float* out_dev,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------
  * Host-side hypercube table build: SRP_PHAT.Map_3D_TDoA + search_cluster
  * (sep/Traditional_SP/SRP_Prunning.py:277-344).  Pure CPU code (no device needed).
  *   offsets [Lx][Ly][Lz][D] int64  quantised TDoA vector of every voxel (:327-331)

@@ -210,3 +210,52 @@ def test_c5_stress_subset_parity(cuda_device):
         want = np.maximum(want, srp_oracle.contract(CC, node.grids[sel], scene.mic_positions, constants.freq_bins,
                                                     48000, 2048))
     assert np.abs(got[sel] - want).max() <= TOL * got.max()
+
+
+def test_device_greedy_selection_equals_host(cuda_device, desk):
+    """asw_select_patches vs the host restatement of local_source_adaptive on the same maps and peaks:
+    integer outputs, bit-exact (offsets, widths, order, peak positions), and the lazily built area points
+    equal the host ones; then the device-built shift table stacks the same tensors."""
+    g, scene, mix, ma = desk
+    node = ma.SRP_node
+    from acousticswarms_speech_b200.pipeline import FrontEnd
+    fe = FrontEnd(node)
+    mixes = np.stack([mix, synth.mixture(scene, 5, mix.shape[1], seed=31), synth.mixture(scene, 2, mix.shape[1], seed=32),
+                      np.zeros_like(mix), synth.mixture(scene, 8, mix.shape[1], seed=33)])
+    x = torch.from_numpy(mixes).cuda()
+    smap, _, _ = fe.score(x)
+    dev_lists = fe.prune(smap)
+    host_lists = fe.prune_host_greedy(smap)
+    for d, h in zip(dev_lists, host_lists):
+        assert len(d) == len(h)
+        for a, b in zip(d, h):
+            assert np.array_equal(a.sample_offset, b.sample_offset) and a.sample_offset.dtype == np.int64
+            assert np.array_equal(a.width_list, b.width_list)
+            assert np.array_equal(a.peak_pos, b.peak_pos)
+    for a, b in zip(dev_lists[0][:3], host_lists[0][:3]):
+        assert np.array_equal(a.area_points, b.area_points)       # built lazily by the same host routine
+    # golden: the reference's own patches for mixture 0 (when its peak set had no near-tie difference)
+    if [int(i) for i in g["peaks"]] == fe.find_peaks(smap[:1])[0][0]:
+        assert np.array_equal(np.array([p.sample_offset for p in dev_lists[0]]), g["patch_offsets"])
+    # device shift table -> counted shift-stack == oracle shift of every selected patch, in order
+    n, off, wid, pk = fe.select(smap)
+    cap = 5 * 64
+    shifts, mi, ntot = fe.shift_table(n, off, cap)
+    total = int(ntot[0])
+    assert total == sum(len(d) for d in dev_lists)
+    want_shifts, want_mi = fe.patch_table(dev_lists)
+    assert np.array_equal(shifts[:total].cpu().numpy(), want_shifts) and np.array_equal(mi[:total].cpu().numpy(), want_mi)
+    fe.net_batch = 32
+    seen = []
+    fe.stack_counted(x, shifts, mi, ntot, cap, consumer=lambda buf, first, k: seen.append((first, buf[:k].cpu().numpy())))
+    checked = 0
+    for first, out in seen:
+        for j in range(out.shape[0]):
+            r = first + j
+            if r < total and r % 7 == 0:
+                assert np.array_equal(out[j], shift_oracle.roll_by_gather(mixes[want_mi[r]], -want_shifts[r].astype(np.int64)))
+                checked += 1
+    assert checked > 5
+    # the drop-in Apply_SRP_PHAT now returns the device-selected patches
+    patches, _ = ma.Apply_SRP_PHAT(torch.from_numpy(mix))
+    assert [list(p.sample_offset) for p in patches] == [list(p.sample_offset) for p in dev_lists[0]]
