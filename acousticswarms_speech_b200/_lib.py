@@ -57,8 +57,8 @@ def load():
     lib.asw_peaks_create.argtypes = [c.POINTER(vp), i32, i32, i32, i32, i32, vp, vp, vp, c.c_double]
     lib.asw_peaks_destroy.argtypes = [vp]
     lib.asw_peaks_find.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp]
-    lib.asw_select_create.argtypes = [c.POINTER(vp), i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp,
-                                      i32, i32, i32]
+    lib.asw_select_create.argtypes = [c.POINTER(vp), i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32,
+                                      i32, vp, vp, vp, vp, i32, i32, i32]
     lib.asw_select_destroy.argtypes = [vp]
     lib.asw_select_patches.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp, vp, vp, i32, vp]
     lib.asw_build_shift_table.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp]

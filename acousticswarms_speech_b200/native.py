@@ -184,13 +184,21 @@ class NativeSelect:
         Ny1, Nx1, Nz1, _ = Offset_1.shape
         assert Nz1 == Nz and D == self.D
         o5 = Offset_5.reshape(-1, D)
-        order = np.argsort(o5[:, 0], kind="stable")
+        # bucket grid over the integer parts of the first two TDoA coordinates
+        f0 = np.floor(o5[:, 0]).astype(np.int64)
+        f1 = np.floor(o5[:, 1]).astype(np.int64) if D >= 2 else np.zeros(o5.shape[0], dtype=np.int64)
+        b0min, b1min = int(f0.min()), int(f1.min())
+        NB0, NB1 = int(f0.max()) - b0min + 1, int(f1.max()) - b1min + 1
+        key = (f0 - b0min) * NB1 + (f1 - b1min)
+        order = np.argsort(key, kind="stable")
+        bucket_start = np.ascontiguousarray(
+            np.searchsorted(key[order], np.arange(NB0 * NB1 + 1), side="left").astype(np.int32))
         iy, ix, iz = np.unravel_index(np.arange(o5.shape[0]), (Ny5, Nx5, Nz))
         ok = (5 * iy < Ny1) & (5 * ix < Nx1)
         o1 = np.full(o5.shape, np.nan)
         o1[ok] = Offset_1[5 * iy[ok], 5 * ix[ok], iz[ok]]
-        off5_sorted = np.ascontiguousarray(o5[order].T)
-        off1_at5 = np.ascontiguousarray(o1[order].T)
+        off5_sorted = np.ascontiguousarray(o5[order])
+        off1_at5 = np.ascontiguousarray(o1[order])
         vox5 = np.ascontiguousarray((iy * Nx5 + ix)[order].astype(np.int32))
         r = Range_spk
         xx5 = np.ascontiguousarray(np.arange(r[0], r[1], 0.05))
@@ -202,7 +210,8 @@ class NativeSelect:
         self._h = ctypes.c_void_p()
         _lib.check(self.lib.asw_select_create(ctypes.byref(self._h), self.device.index or 0, self.G, self.D, int(width),
                                               cl.ctypes.data, off5_sorted.ctypes.data, off1_at5.ctypes.data,
-                                              vox5.ctypes.data, o5.shape[0], Nx5, Ny5, xx5.ctypes.data,
+                                              vox5.ctypes.data, bucket_start.ctypes.data, b0min, b1min, NB0, NB1,
+                                              o5.shape[0], Nx5, Ny5, xx5.ctypes.data,
                                               yy5.ctypes.data, axis.ctypes.data, off1.ctypes.data, Ny1, Nx1, Nz))
 
     def close(self):

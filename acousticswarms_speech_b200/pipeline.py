@@ -28,14 +28,17 @@ class FrontEnd:
         self._map = None
 
     # ---- scoring ---------------------------------------------------------------------------------
-    def score(self, mix_dev):
-        """(B, M, T) float32 CUDA -> (map (B, G), top values (B, K), top indices (B, K))."""
+    def score(self, mix_dev, out=None):
+        """(B, M, T) float32 CUDA -> (map (B, G), top values (B, K), top indices (B, K)).
+        ``out``: caller-owned map buffer (for pipelines that keep several steps in flight)."""
         B, M, T = mix_dev.shape
-        if self._map is None or self._map.shape[0] != B:
-            self._map = torch.empty((B, self.h.G), device=self.device, dtype=torch.float32)
-        self.h.score(mix_dev, window_length(T), out=self._map)
-        val, idx = native.map_topk(self._map, min(self.topk, 1024))
-        return self._map, val, idx
+        if out is None:
+            if self._map is None or self._map.shape[0] != B:
+                self._map = torch.empty((B, self.h.G), device=self.device, dtype=torch.float32)
+            out = self._map
+        self.h.score(mix_dev, window_length(T), out=out)
+        val, idx = native.map_topk(out, min(self.topk, 1024))
+        return out, val, idx
 
     # ---- shift-stack -----------------------------------------------------------------------------
     def _ring(self, M, T):

@@ -11,8 +11,8 @@ SURVEY.md section 8d (7 mics, 5 speakers, 3 s @ 48 kHz, one desk geometry, G ~ 2
     asw_peaks_find (fill_powermap + find_valid_peak_new: thresholded 3-D local maxima -> peak hypercubes)
     asw_shift_stack of every coarse hypercube patch of every mixture, 128 patches per launch into a
                   ring of (128, M, T) network-input buffers.
-The coarse patch lists come from the reference's greedy selection (local_source_adaptive) run on each
-mixture's device-picked peaks during setup (host code, outside the timed region).
+    asw_select_patches + asw_build_shift_table (local_source_adaptive -> dense per-step patch table)
+Every step selects its own patches on the device; nothing in the timed region runs on the host.
 `value` starts with inputs resident in HBM; `e2e` starts from pinned host buffers and ends with the
 maps / top-K back on the host.  Prints ONE JSON line on rank 0.
 """
@@ -43,9 +43,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="mixtures per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fused-norm", action="store_true", help="shift-stack fused with normalize_input")
-    ap.add_argument("--streams", type=int, default=2, choices=[1, 2],
-                    help="2: scoring (SM/shared-memory bound) of step i+1 overlaps the shift-stack (HBM bound) of step i")
+    ap.add_argument("--streams", type=int, default=3, choices=[1, 3],
+                    help="3: scoring (SM/shared-memory bound), pruning (latency bound, B CTAs) and shift-stack (HBM "
+                         "bound) of consecutive steps run on their own streams and overlap; 1: fully serial")
     return ap.parse_args()
 
 
@@ -164,7 +164,7 @@ def run_reference(args, rank):
 def run_b200(args, rank, world):
     import torch
     import torch.distributed as dist
-    from acousticswarms_speech_b200 import _lib, synth
+    from acousticswarms_speech_b200 import _lib, native, synth
     from acousticswarms_speech_b200.constants import SRP_THRESHOLDS, freq_bins, n_fft
     from acousticswarms_speech_b200.pipeline import FrontEnd
     from acousticswarms_speech_b200.srp_phat import SRP_PHAT
@@ -191,11 +191,18 @@ def run_b200(args, rank, world):
     # setup (untimed): coarse patch lists = the reference's pruning on each mixture's map
     smap, _, _ = fe.score(mix_dev)
     torch.cuda.synchronize()
-    patch_lists = fe.prune(smap)          # peaks on the device, greedy hypercube selection on the host
-    shifts_np, mi_np = fe.patch_table(patch_lists)
-    N = shifts_np.shape[0]
-    shifts_dev = torch.from_numpy(shifts_np).to(dev)
-    mi_dev = torch.from_numpy(mi_np).to(dev)
+    # warm-up pass: how many coarse patches this workload selects (sizes the shift-table capacity; the
+    # timed steps select their own patches on the device and never read these lists)
+    n_sel, _, _, _ = fe.select(smap)
+    N = int(n_sel.clamp(max=node.native_select.max_patches).sum())
+    MAXPATCH = node.native_select.max_patches
+    cap = min(B * MAXPATCH, ((int(N * 1.25) + fe.net_batch - 1) // fe.net_batch) * fe.net_batch)
+    # two shift tables: the scoring of step i+1 rebuilds one while the shift-stack of step i reads the other
+    tables = [(torch.zeros((cap, M), device=dev, dtype=torch.int32), torch.zeros((cap,), device=dev, dtype=torch.int32),
+               torch.zeros((1,), device=dev, dtype=torch.int32)) for _ in range(2)]
+    table_free = [None, None]
+    step_no = [0]
+    sel_pin = torch.empty((B, MAXPATCH * (M + 1) + 1), dtype=torch.int32).pin_memory()
     K = fe.topk
     map_pin = torch.empty((B, G), dtype=torch.float32).pin_memory()
     val_pin = torch.empty((B, K), dtype=torch.float32).pin_memory()
@@ -209,15 +216,24 @@ def run_b200(args, rank, world):
     gathered = torch.empty((world * B, 2 * K), device=dev) if world > 1 else None
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
 
-    stack_stream = torch.cuda.Stream(device=dev) if args.streams == 2 else None
+    stack_stream = torch.cuda.Stream(device=dev) if args.streams == 3 else None
+    prune_stream = torch.cuda.Stream(device=dev) if args.streams == 3 else None
+    maps = [torch.empty((B, G), device=dev) for _ in range(2)]     # step i+1 scores while step i is pruned
+    map_free = [None, None]
 
     def compute(src, events=None, to_host=False):
+        """One step: score -> top-K -> peak picking -> greedy patch selection -> shift table -> shift-stack.
+        With three streams the stages of consecutive steps software-pipeline (every step still consumes its
+        own scores: prune(i) waits for score(i), stack(i) waits for prune(i))."""
         nonlocal stack_stream
-        """One step.  With two streams the scoring half runs on the current stream and the shift-stack
-        half on `stack_stream` behind an event, so consecutive steps software-pipeline."""
-        m, val, idx = fe.score(src)
+        main = torch.cuda.current_stream(dev)
+        slot = step_no[0] & 1
+        step_no[0] += 1
+        if map_free[slot] is not None:
+            main.wait_event(map_free[slot])              # prune of step i-2 is done with this map buffer
+        m, val, idx = fe.score(src, out=maps[slot])
         if world > 1:          # the one collective of the path: every rank learns every mixture's top-K
-            torch.cuda.current_stream(dev).wait_stream(comm_stream)   # previous step's gather has read `pack`
+            main.wait_stream(comm_stream)                # previous step's gather has read `pack`
             pack[:, :K] = val
             pack[:, K:] = idx.view(torch.float32)
             packed = torch.cuda.Event()
@@ -225,26 +241,42 @@ def run_b200(args, rank, world):
             comm_stream.wait_event(packed)
             with torch.cuda.stream(comm_stream):
                 dist.all_gather_into_tensor(gathered, pack)
-        peaks, count, _ = node.native_peaks.find(m)       # fill_powermap + find_valid_peak_new on the device
-        if to_host:
-            peaks_pin.copy_(peaks, non_blocking=True)
-            count_pin.copy_(count, non_blocking=True)
-            map_pin.copy_(m, non_blocking=True)
-            val_pin.copy_(val, non_blocking=True)
-            idx_pin.copy_(idx, non_blocking=True)
-        if stack_stream is None:
-            fe.stack(src, shifts_dev, mi_dev, fused_norm=args.fused_norm, events=events)
-        else:
-            main = torch.cuda.current_stream(dev)
-            scored = torch.cuda.Event()
-            scored.record(main)
-            stack_stream.wait_event(scored)      # the patch list of a step depends on its own scores
-            with torch.cuda.stream(stack_stream):
-                fe.stack(src, shifts_dev, mi_dev, fused_norm=args.fused_norm, events=events)
+        serial = stack_stream is None
+        pstream = main if serial else prune_stream
+        sstream = main if serial else stack_stream
+        scored = torch.cuda.Event()
+        scored.record(main)
+        pstream.wait_event(scored)
+        with torch.cuda.stream(pstream):
+            shifts_dev, mi_dev, ntot_dev = tables[slot]
+            if table_free[slot] is not None:
+                pstream.wait_event(table_free[slot])     # stack of step i-2 is done with this table
+            peaks, count, _ = node.native_peaks.find(m)                            # fill_powermap + find_valid_peak_new
+            n_p, off_p, wid_p, pk_p = node.native_select.select(m, peaks, count)   # local_source_adaptive
+            native.build_shift_table(n_p, off_p, cap, shifts_dev, mi_dev, ntot_dev)
+            if to_host:
+                sel_pin[:, 0].copy_(n_p, non_blocking=True)
+                sel_pin[:, 1:1 + MAXPATCH * (M - 1)].copy_(off_p.view(B, -1), non_blocking=True)
+                sel_pin[:, 1 + MAXPATCH * (M - 1):1 + MAXPATCH * M].copy_(wid_p, non_blocking=True)
+                sel_pin[:, 1 + MAXPATCH * M:].copy_(pk_p, non_blocking=True)
+                peaks_pin.copy_(peaks, non_blocking=True)
+                count_pin.copy_(count, non_blocking=True)
+                map_pin.copy_(m, non_blocking=True)
+                val_pin.copy_(val, non_blocking=True)
+                idx_pin.copy_(idx, non_blocking=True)
+            pruned = torch.cuda.Event()
+            pruned.record(pstream)
+            map_free[slot] = pruned
+        sstream.wait_event(pruned)
+        with torch.cuda.stream(sstream):
+            fe.stack_counted(src, shifts_dev, mi_dev, ntot_dev, cap, events=events)
+            table_free[slot] = torch.cuda.Event()
+            table_free[slot].record(sstream)
 
     def join_streams():
         nonlocal stack_stream
         if stack_stream is not None:
+            torch.cuda.current_stream(dev).wait_stream(prune_stream)
             torch.cuda.current_stream(dev).wait_stream(stack_stream)
         if comm_stream is not None:
             torch.cuda.current_stream(dev).wait_stream(comm_stream)
@@ -325,8 +357,10 @@ def run_b200(args, rank, world):
     timed(max(2, min(args.steps, 5)), events=events)
     stack_stream = saved_stream
     torch.cuda.synchronize()
+    per = (cap + fe.net_batch - 1) // fe.net_batch                  # launches per step
+    valid = [max(0, min(fe.net_batch, N - (j % per) * fe.net_batch)) for j in range(len(events))]
     k_ms = [a.elapsed_time(b) for a, b, _ in events]
-    k_bytes = [4.0 * n * M * T for _, _, n in events]
+    k_bytes = [4.0 * v * M * T for v in valid]
     full = [(t, by) for t, by in zip(k_ms, k_bytes) if by == 4.0 * fe.net_batch * M * T] or list(zip(k_ms, k_bytes))
     k_avg_ms = sum(t for t, _ in full) / len(full)
     k_avg_bytes = sum(by for _, by in full) / len(full)
@@ -350,15 +384,17 @@ def run_b200(args, rank, world):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "mixtures_per_gpu_per_step": B, "hypercubes": G, "mics": M, "speakers": N_SPK,
                    "samples": T, "fs": FS, "coarse_patches_per_step_per_gpu": N, "net_batch": fe.net_batch,
-                   "fused_norm": bool(args.fused_norm), "streams": args.streams, "parallelism": f"mixtures sharded over {world} GPU(s)",
+                   "streams": args.streams, "parallelism": f"mixtures sharded over {world} GPU(s)",
                    "l2": f"inputs {B * M * T * 4 / 1e6:.0f} MB + stacked output {N * M * T * 4 / 1e9:.2f} GB per step "
                          "exceed the 126 MB L2 (no explicit flush)",
-                   "prune": "peak picking (fill_powermap + find_valid_peak_new) on the device inside the step; the "
-                            "greedy hypercube selection (local_source_adaptive) runs on the host during setup, "
-                            "outside the timed region, and fixes the patch lists the shift-stack uses"},
+                   "shift_table_capacity": cap,
+                   "prune": "peak picking (fill_powermap + find_valid_peak_new) and greedy hypercube selection "
+                            "(local_source_adaptive) run on the device inside every step; the shift-stack reads "
+                            "the device-built patch table of its own step (rows beyond the device count are "
+                            "skipped), no host work in the timed region"},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "pipeline": "pinned host -> device copy of step i+1 overlaps the kernels of step i (2 buffers)",
-                "h2d_bytes_per_step": int(B * M * T * 4), "d2h_bytes_per_step": int(B * G * 4 + B * K * 8 + B * MAXP * 4 + B * 4)},
+                "h2d_bytes_per_step": int(B * M * T * 4), "d2h_bytes_per_step": int(B * G * 4 + B * K * 8 + B * MAXP * 4 + B * 4 + sel_pin.numel() * 4)},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "shift_stack_vec_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "peak_kind": pk_kind + " (copy, burst)",

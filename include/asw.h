@@ -155,11 +155,12 @@ int asw_peaks_find(asw_peaks_t* h, const float* map_dev, int B, int32_t* peaks_d
  * asw_peaks_find.  Decisions (trimming, covered peaks, "is any 1 cm voxel inside") are evaluated in
  * double on the same float64 volumes the reference builds in SRP_PHAT.__init__ (:148-170).
  *   cluster_offsets [G][D] int32    quantised TDoA vector of every cluster (Grid_cluster.sample_offset)
- *   off5_sorted     [D][n5] float64 Offset_5 flattened in C order ([y][x][z]), voxels sorted by
- *                                   coordinate 0, stored coordinate-major
- *   off1_at5        [D][n5] float64 Offset_1 at the 1 cm voxel (5*iy, 5*ix, iz) coinciding with each of
+ *   off5_sorted     [n5][D] float64 Offset_5 voxel records ordered by bucket
+ *                                   (floor(o0) - b0min) * NB1 + (floor(o1) - b1min)   (o1 bucket 0 if D == 1)
+ *   off1_at5        [n5][D] float64 Offset_1 at the 1 cm voxel (5*iy, 5*ix, iz) coinciding with each of
  *                                   those 5 cm voxels, same order (NaN where it does not exist)
- *   vox5            [n5] int32      iy * Nx5 + ix of the sorted voxels
+ *   vox5            [n5] int32      iy * Nx5 + ix of the ordered voxels
+ *   bucket_start    [NB0*NB1 + 1] int32 first record of every bucket
  *   xx5, yy5        float64         the 5 cm grid coordinates (np.arange, :149-150)
  *   axis_range4     {x0, x1, y0, y1} (Axis_range, :146)
  *   off1            [Ny1][Nx1][Nz][D] float64  Offset_1 (:167-170)
@@ -170,9 +171,10 @@ int asw_peaks_find(asw_peaks_t* h, const float* map_dev, int B, int32_t* peaks_d
  * Patch.area_points is not produced (the host builds it on demand for the patches that get subdivided). */
 typedef struct asw_select asw_select_t;
 int asw_select_create(asw_select_t** out, int device, int G, int D, int W, const int32_t* cluster_offsets,
-                      const double* off5_sorted, const double* off1_at5, const int32_t* vox5, int n5, int Nx5,
-                      int Ny5, const double* xx5, const double* yy5, const double* axis_range4,
-                      const double* off1, int Ny1, int Nx1, int Nz);
+                      const double* off5_sorted, const double* off1_at5, const int32_t* vox5,
+                      const int32_t* bucket_start, int b0min, int b1min, int NB0, int NB1, int n5, int Nx5, int Ny5,
+                      const double* xx5, const double* yy5, const double* axis_range4, const double* off1, int Ny1,
+                      int Nx1, int Nz);
 int asw_select_destroy(asw_select_t* h);
 int asw_select_patches(asw_select_t* h, const float* map_dev, const int32_t* peaks_dev, int max_peaks,
                        const int32_t* count_dev, int B, int32_t* out_count_dev, int32_t* out_offsets_dev,
