@@ -91,6 +91,9 @@ class FrontEnd:
         hypercube selection, SRP_Prunning.py:500-643) -> list (per mixture) of list[Patch]."""
         n, off, wid, pk = self.select(map_dev)
         n_h, off_h, wid_h, pk_h = n.cpu().numpy(), off.cpu().numpy(), wid.cpu().numpy(), pk.cpu().numpy()
+        if n_h.max(initial=0) > off_h.shape[1] or self._last_peak_count.max().item() > self.node.native_peaks.max_peaks:
+            raise native._lib.AswError("peak or patch list capacity exceeded: results would be truncated "
+                                       "(raise max_peaks / max_patches)")
         return [self.node.patches_from_device(min(int(n_h[b]), off_h.shape[1]), off_h[b], wid_h[b], pk_h[b])
                 for b in range(map_dev.shape[0])]
 
@@ -101,6 +104,7 @@ class FrontEnd:
     def select(self, map_dev):
         """Device peak picking + greedy selection -> (n (B,), offsets (B, P, D), widths (B, P), peak ids (B, P))."""
         peaks, count, _ = self.node.native_peaks.find(map_dev)
+        self._last_peak_count = count
         return self.node.native_select.select(map_dev, peaks, count)
 
     def shift_table(self, n, offsets, capacity):

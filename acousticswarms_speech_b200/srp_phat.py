@@ -367,6 +367,8 @@ class SRP_PHAT(object):
         m = self.SRP_map.to(torch.float32).unsqueeze(0).contiguous()
         peaks, count, _ = self.native_peaks.find(m)
         n, off, wid, pk = self.native_select.select(m, peaks, count)
+        if int(count[0]) > self.native_peaks.max_peaks:
+            raise _lib.AswError(f"{int(count[0])} peak clusters exceed the device list of {self.native_peaks.max_peaks}")
         n_h = int(n[0])
         if n_h > self.native_select.max_patches:
             raise _lib.AswError(f"{n_h} patches exceed the device list of {self.native_select.max_patches}")

@@ -259,3 +259,51 @@ def test_device_greedy_selection_equals_host(cuda_device, desk):
     # the drop-in Apply_SRP_PHAT now returns the device-selected patches
     patches, _ = ma.Apply_SRP_PHAT(torch.from_numpy(mix))
     assert [list(p.sample_offset) for p in patches] == [list(p.sample_offset) for p in dev_lists[0]]
+
+
+class OracleSpot:
+    """Oracle twin of DataParallelSpotModel(MeanOverMics): shift -> normalize_input -> net -> unnormalize."""
+
+    def shift_and_sep(self, mix, patch_list, Strict=0, save_input=False):
+        mix = np.asarray(mix)
+        if len(patch_list) == 0:
+            return np.zeros((0, mix.shape[1]), dtype=np.float32)
+        stacked = shift_oracle.shift_stack(mix, [p.sample_offset for p in patch_list])
+        dn, mu, sd = shift_oracle.normalize_input(stacked)
+        net = dn.mean(1) if Strict == 0 else 2 * dn[:, 0]
+        return (net * sd[:, 0] + mu[:, 0]).astype(np.float32)
+
+
+def test_spotform_big_and_small_patch_drop_in(cuda_device, desk):
+    """Mic_Array.Spotform_Big_Patch / Spotform_Small_Patch_Parallel (sep/Mic_Array.py:196-395) with a stand-in
+    network on the device path vs the oracle's restatement of binary_search_baseline / search_area on the
+    reference's golden patches."""
+    import copy
+    from oracle import subdivide_oracle
+    g, scene, mix, ma = desk
+    from acousticswarms_speech_b200.spot import DataParallelSpotModel
+    from acousticswarms_speech_b200.patch import Patch
+    spot = DataParallelSpotModel(MeanOverMics(), batch_size=128)
+    patches, _ = ma.Apply_SRP_PHAT(torch.from_numpy(mix))
+    if not np.array_equal(np.array([p.sample_offset for p in patches]), g["patch_offsets"]):
+        pytest.skip("peak set differs from the golden one at a near-tie")
+    # coarse stage
+    kept = ma.Spotform_Big_Patch(torch.from_numpy(mix), copy.deepcopy(patches), spot)
+    opatches = [prune_oracle.Patch(p.sample_offset.copy(), p.width_list.copy(), p.area_points, p.peak_pos) for p in patches]
+    sep = OracleSpot().shift_and_sep(mix, opatches, Strict=0)
+    okept, _, othr = subdivide_oracle.big_patch_select(sep, opatches, scene.mic_positions)
+    assert [list(p.sample_offset) for p in kept] == [list(p.sample_offset) for p in okept]
+    assert abs(ma.Relative_Threshold - othr) < 1e-12
+    assert 0 < len(kept) <= 30
+    # fine stage: the patch list that feeds shift_and_sep(Strict=1)
+    total, index, _, _ = ma.small_patch_list(copy.deepcopy(kept[:4]))
+    ototal, oindex = subdivide_oracle.small_patch_list(copy.deepcopy(okept[:4]), scene.mic_positions)
+    assert index == oindex
+    assert [list(p.sample_offset) for p in total] == [list(p.sample_offset) for p in ototal]
+    assert [list(p.width_list) for p in total] == [list(p.width_list) for p in ototal]
+    assert all(max(p.width_list) <= 4 for p in total)
+    # and the whole method runs and returns well-formed candidates
+    pairs = ma.Spotform_Small_Patch_Parallel(torch.from_numpy(mix), copy.deepcopy(kept[:4]), spot)
+    for patch_center, audio, power, tag, offs, label in pairs:
+        assert isinstance(patch_center, Patch) and audio.shape == (mix.shape[1],) and power > 0
+        assert set(offs) == {"audio_offset", "localization_offset"} and label == -1
