@@ -450,6 +450,14 @@ int asw_shift_stack(const float* mix_dev, const int32_t* shifts_dev, const int32
     return launch_shift_stack(mix_dev, shifts_dev, mix_index_dev, N, B, M, T, out_dev, (cudaStream_t)stream);
 }
 
+int asw_pcm16_to_f32(const int16_t* pcm_dev, float* out_dev, long long n, void* stream) {
+    if (!pcm_dev || !out_dev || n < 0) {
+        set_error("asw_pcm16_to_f32: null buffer or negative length");
+        return ASW_ERR_ARG;
+    }
+    return launch_pcm16_to_f32(reinterpret_cast<const short*>(pcm_dev), out_dev, (size_t)n, (cudaStream_t)stream);
+}
+
 int asw_shift_stack_counted(const float* mix_dev, const int32_t* shifts_dev, const int32_t* mix_index_dev,
                             const int32_t* n_valid_dev, int n_base, int N, int B, int M, int T, float* out_dev,
                             void* stream) {

@@ -91,6 +91,7 @@ int launch_topk(const float* map, int B, int G, int K, int idx_offset, float* va
 
 int launch_shift_stack(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int B, int M,
                        int T, float* out, cudaStream_t s);
+int launch_pcm16_to_f32(const short* in, float* out, size_t n, cudaStream_t s);
 int launch_shift_stack_counted(const float* mix, const int32_t* shifts, const int32_t* mix_index, const int32_t* n_valid,
                                int n_base, int N, int B, int M, int T, float* out, cudaStream_t s);
 int launch_shift_stack_norm(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int B,

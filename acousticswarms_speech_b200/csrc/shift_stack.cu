@@ -196,6 +196,31 @@ __global__ void __launch_bounds__(kThreads) shift_ref_stats_kernel(const float* 
     }
 }
 
+// int16 PCM -> float32 in [-1, 1): x / 32768, the conversion soundfile/librosa apply when the reference loads
+// its PCM_16 wav files (sep/helpers/utils.py read_audio_file); exact in float32.
+__global__ void __launch_bounds__(256) pcm16_to_f32_kernel(const short* __restrict__ in, float* __restrict__ out,
+                                                           size_t n) {
+    const size_t n8 = n >> 3;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(in) + i);
+        const short* s = reinterpret_cast<const short*>(&v);
+        float4 a, b;
+        a.x = (float)s[0] * (1.f / 32768.f);
+        a.y = (float)s[1] * (1.f / 32768.f);
+        a.z = (float)s[2] * (1.f / 32768.f);
+        a.w = (float)s[3] * (1.f / 32768.f);
+        b.x = (float)s[4] * (1.f / 32768.f);
+        b.y = (float)s[5] * (1.f / 32768.f);
+        b.z = (float)s[6] * (1.f / 32768.f);
+        b.w = (float)s[7] * (1.f / 32768.f);
+        reinterpret_cast<float4*>(out)[2 * i] = a;
+        reinterpret_cast<float4*>(out)[2 * i + 1] = b;
+    }
+    for (size_t i = (n8 << 3) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (float)in[i] * (1.f / 32768.f);
+}
+
 template <bool NORM>
 int launch_rows(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int M, int T, float* out,
                 const double* work, float* means, float* stds, cudaStream_t s, const int32_t* n_valid = nullptr,
@@ -231,6 +256,17 @@ int launch_shift_stack(const float* mix, const int32_t* shifts, const int32_t* m
     (void)B;
     if (N == 0) return ASW_OK;
     return launch_rows<false>(mix, shifts, mix_index, N, M, T, out, nullptr, nullptr, nullptr, s);
+}
+
+int launch_pcm16_to_f32(const short* in, float* out, size_t n, cudaStream_t s) {
+    if (n == 0) return ASW_OK;
+    if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) {
+        set_error("pcm16_to_f32: buffers must be 16-byte aligned");
+        return ASW_ERR_ARG;
+    }
+    pcm16_to_f32_kernel<<<kNumSms * 8, 256, 0, s>>>(in, out, n);
+    ASW_LAUNCH_CHECK("pcm16_to_f32_kernel");
+    return ASW_OK;
 }
 
 int launch_shift_stack_counted(const float* mix, const int32_t* shifts, const int32_t* mix_index, const int32_t* n_valid,

@@ -346,6 +346,20 @@ def shift_stack_norm(mix, shifts, mix_index=None, out=None):
     return out[:N], means.view(N, 1, 1), stds.view(N, 1, 1)
 
 
+def pcm16_to_f32(pcm, out=None):
+    """int16 CUDA tensor -> float32 = pcm / 32768 (what soundfile/librosa produce for PCM_16 files)."""
+    _require_cuda(pcm, "pcm", torch.int16)
+    if out is None:
+        out = torch.empty(pcm.shape, device=pcm.device, dtype=torch.float32)
+    else:
+        _require_cuda(out, "out", torch.float32)
+        if out.numel() != pcm.numel():
+            raise _lib.AswError("out must have as many elements as pcm")
+    if pcm.numel():
+        _lib.check(_lib.load().asw_pcm16_to_f32(_ptr(pcm), _ptr(out), pcm.numel(), _stream(pcm.device)))
+    return out
+
+
 def offsets_to_shifts(offsets):
     """Patch.sample_offset list -> (N, M) int32 read offsets: r[0] = 0, r[c] = round_half_even(float32(off[c-1]))
     (sep/training/JointModel/network.py:81-82)."""

@@ -139,7 +139,8 @@ def run_reference(args, rank):
     from acousticswarms_speech_b200 import synth
     scene, geo, ref = cpu_reference_setup()
     G = geo.grids.shape[0]
-    mixes = [synth.mixture(scene, N_SPK, T_SAMPLES, seed=1000 + i) for i in range(max(1, min(4, args.steps)))]
+    mixes = [(np.clip(np.rint(synth.mixture(scene, N_SPK, T_SAMPLES, seed=1000 + i) * 32768.0), -32768, 32767)
+              / 32768.0).astype(np.float32) for i in range(max(1, min(4, args.steps)))]     # 16-bit PCM content
     for i in range(max(1, min(args.warmup, 1))):
         cpu_reference_step(ref, mixes[0])
     t0 = time.perf_counter()
@@ -184,8 +185,12 @@ def run_b200(args, rank, world):
     M, T = N_MICS, T_SAMPLES
 
     # synthetic mixtures: every rank gets its own B mixtures (weak scaling over mixtures)
-    mix_host = torch.from_numpy(synth.mixtures(scene, N_SPK, T, seeds=[10_000 * rank + 100 + b for b in range(B)]))
+    # 16-bit PCM content (what the reference's PCM_16 wav datasets hold), carried as float32 = pcm / 32768
+    raw = synth.mixtures(scene, N_SPK, T, seeds=[10_000 * rank + 100 + b for b in range(B)])
+    pcm_host = torch.from_numpy(np.clip(np.rint(raw * 32768.0), -32768, 32767).astype(np.int16))
+    mix_host = pcm_host.to(torch.float32) / 32768.0
     mix_pin = mix_host.pin_memory()
+    pcm_pin = pcm_host.pin_memory()
     mix_dev = mix_pin.to(dev)
 
     # setup (untimed): coarse patch lists = the reference's pruning on each mixture's map
@@ -309,26 +314,37 @@ def run_b200(args, rank, world):
     # e2e: every step copies its B mixtures from pinned host memory (double-buffered on a copy stream so
     # the PCIe transfer of step i+1 overlaps the kernels of step i) and returns maps + top-K to the host.
     copy_stream = torch.cuda.Stream(device=dev)
-    in_bufs = [torch.empty_like(mix_dev), torch.empty_like(mix_dev)]
+    NBUF = 3                  # input ring: upload(i+1) may run while step i computes and step i-1 still stacks
+    in_bufs = [torch.empty_like(mix_dev) for _ in range(NBUF)]
 
-    def timed_e2e(n_steps):
+    pcm_bufs = [torch.empty((B, M, T), device=dev, dtype=torch.int16) for _ in range(NBUF)]
+
+    def timed_e2e(n_steps, pcm=False):
+        """pcm=True: the host ships int16 PCM (half the PCIe bytes) and asw_pcm16_to_f32 expands it on the device."""
         barrier()
         main = torch.cuda.current_stream(dev)
-        copied = [torch.cuda.Event(), torch.cuda.Event()]
-        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        copied = [torch.cuda.Event() for _ in range(NBUF)]
+        consumed = [torch.cuda.Event() for _ in range(NBUF)]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         copy_stream.wait_event(e0)
+        def upload(slot):
+            if pcm:
+                pcm_bufs[slot].copy_(pcm_pin, non_blocking=True)
+                native.pcm16_to_f32(pcm_bufs[slot], in_bufs[slot])
+            else:
+                in_bufs[slot].copy_(mix_pin, non_blocking=True)
+
         with torch.cuda.stream(copy_stream):
-            in_bufs[0].copy_(mix_pin, non_blocking=True)
+            upload(0)
             copied[0].record()
         for i in range(n_steps):
-            cur, nxt = i & 1, (i + 1) & 1
+            cur, nxt = i % NBUF, (i + 1) % NBUF
             if i + 1 < n_steps:
                 with torch.cuda.stream(copy_stream):
-                    if i >= 1:
-                        copy_stream.wait_event(consumed[nxt])
-                    in_bufs[nxt].copy_(mix_pin, non_blocking=True)
+                    if i + 1 >= NBUF:
+                        copy_stream.wait_event(consumed[nxt])   # step i+1-NBUF was the last user of this buffer
+                    upload(nxt)
                     copied[nxt].record()
             main.wait_event(copied[cur])
             compute(in_bufs[cur], to_host=True)
@@ -367,6 +383,8 @@ def run_b200(args, rank, world):
     # end to end from pinned host memory
     timed_e2e(2)
     ms_e2e = timed_e2e(args.steps)
+    timed_e2e(2, pcm=True)
+    ms_e2e_pcm = timed_e2e(args.steps, pcm=True)
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -381,7 +399,7 @@ def run_b200(args, rank, world):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "f32", "data": "synthetic (16-bit PCM content carried as float32)",
         "config": {"workload": WORKLOAD, "mixtures_per_gpu_per_step": B, "hypercubes": G, "mics": M, "speakers": N_SPK,
                    "samples": T, "fs": FS, "coarse_patches_per_step_per_gpu": N, "net_batch": fe.net_batch,
                    "streams": args.streams, "parallelism": f"mixtures sharded over {world} GPU(s)",
@@ -393,8 +411,12 @@ def run_b200(args, rank, world):
                             "the device-built patch table of its own step (rows beyond the device count are "
                             "skipped), no host work in the timed region"},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                "pipeline": "pinned host -> device copy of step i+1 overlaps the kernels of step i (2 buffers)",
+                "pipeline": "pinned host -> device copy of step i+1 overlaps the kernels of step i (3 input buffers)",
                 "h2d_bytes_per_step": int(B * M * T * 4), "d2h_bytes_per_step": int(B * G * 4 + B * K * 8 + B * MAXP * 4 + B * 4 + sel_pin.numel() * 4)},
+        "e2e_pcm16": {"value": per_step / (ms_e2e_pcm / args.steps / 1e3), "unit": UNIT, "ms_per_step": ms_e2e_pcm / args.steps,
+                      "h2d_bytes_per_step": int(B * M * T * 2),
+                      "note": "same step, but the host ships the 16-bit PCM the mixtures consist of and "
+                              "asw_pcm16_to_f32 expands it on the device (PCIe bytes halved); `e2e` above ships float32"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "shift_stack_vec_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "peak_kind": pk_kind + " (copy, burst)",
@@ -412,7 +434,7 @@ def run_b200(args, rank, world):
         try:
             t0 = time.perf_counter()
             _, geo, ref = cpu_reference_setup()
-            mixes = mix_host.numpy()
+            mixes = mix_host.numpy()                                # the same dequantised float32 data
             cpu_reference_step(ref, mixes[0])                     # warm-up
             best = None
             for i in range(3):

@@ -105,6 +105,13 @@ int asw_map_topk(const float* map_dev, int B, int G, int K, int idx_offset,
                  float* val_dev, int32_t* idx_dev, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * PCM16 ingest: out[i] = pcm[i] / 32768 (float32, exact) -- the conversion soundfile/librosa apply when the
+ * reference loads its PCM_16 wav files (sep/helpers/utils.py read_audio_file, sep/eval/get_items.py:10-44).
+ * Lets a caller ship 16-bit audio over PCIe and expand it on the device; the float32 mixture it produces
+ * is what every other entry point consumes.  Buffers must be 16-byte aligned. */
+int asw_pcm16_to_f32(const int16_t* pcm_dev, float* out_dev, long long n, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Shift-and-stack: the loop of DataParallelSpotModel.shift_and_sep
  * (sep/training/JointModel/network.py:75-83) with roll_by_gather (:12-25):
  *     out[n][c][t] = mix[mix_index[n]][c][(t + shifts[n][c]) mod T]

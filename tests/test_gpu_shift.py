@@ -92,3 +92,14 @@ def test_shift_stack_norm(cuda_device):
     assert np.abs(mu.cpu().numpy() - wmu).max() <= 1e-4 * np.abs(wsd).max()
     assert np.abs(sd.cpu().numpy() - wsd).max() <= 1e-4 * np.abs(wsd).max()
     assert np.abs(dn.cpu().numpy() - want).max() <= 1e-4 * np.abs(want).max()
+
+
+def test_pcm16_ingest_is_exact(cuda_device):
+    from acousticswarms_speech_b200 import native
+    rng = np.random.default_rng(2)
+    for n in (0, 1, 7, 8, 4099, 7 * 144000):
+        pcm = rng.integers(-32768, 32768, size=n, dtype=np.int16)
+        if n >= 4:
+            pcm[:4] = [-32768, 32767, 0, -1]
+        got = native.pcm16_to_f32(torch.from_numpy(pcm).cuda()).cpu().numpy()
+        assert np.array_equal(got, pcm.astype(np.float32) / np.float32(32768.0))
