@@ -307,3 +307,28 @@ def test_spotform_big_and_small_patch_drop_in(cuda_device, desk):
     for patch_center, audio, power, tag, offs, label in pairs:
         assert isinstance(patch_center, Patch) and audio.shape == (mix.shape[1],) and power > 0
         assert set(offs) == {"audio_offset", "localization_offset"} and label == -1
+
+
+def test_two_mic_array_end_to_end(cuda_device):
+    """M = 2: one pair, one TDoA dimension -- exercises D = 1 in scoring, peak picking and patch selection."""
+    from acousticswarms_speech_b200.mic_array import Mic_Array
+    from acousticswarms_speech_b200.pipeline import FrontEnd
+    scene = synth.small_scene(n_mics=2, seed=5)
+    scene.mic_positions[1, :2] = [0.0, 0.45]
+    scene.roi = [0.6, 2.0, -1.0, 1.0, 0.0, 0.6]
+    ma = Mic_Array(scene.mic_positions, Spk_Range=scene.roi)
+    node = ma.SRP_node
+    mixes = synth.mixtures(scene, 2, 72000, seeds=[4, 5])
+    fe = FrontEnd(node)
+    smap, _, _ = fe.score(torch.from_numpy(mixes).cuda())
+    maps = smap.cpu().numpy()
+    for b in range(2):
+        want = srp_oracle.score(mixes[b], node.grids, scene.mic_positions, constants.freq_bins, 48000, 2048)
+        assert np.abs(maps[b] - want).max() <= TOL * want.max()
+    dev_lists = fe.prune(smap)
+    host_lists = fe.prune_host_greedy(smap)
+    for d, h in zip(dev_lists, host_lists):
+        assert [list(p.sample_offset) for p in d] == [list(p.sample_offset) for p in h]
+        assert [list(p.width_list) for p in d] == [list(p.width_list) for p in h]
+    patches, _ = ma.Apply_SRP_PHAT(torch.from_numpy(mixes[0]))
+    assert [list(p.sample_offset) for p in patches] == [list(p.sample_offset) for p in dev_lists[0]]

@@ -138,3 +138,27 @@ def test_topk(cuda_device):
     # K > G pads with (-inf, -1)
     val, idx = native.map_topk(torch.from_numpy(m[:, :10].copy()).cuda(), 16)
     assert (idx.cpu().numpy()[:, 10:] == -1).all() and np.isneginf(val.cpu().numpy()[:, 10:]).all()
+
+
+@pytest.mark.parametrize("T", [48001, 48002, 50003])
+def test_misaligned_rows(cuda_device, small, T):
+    """T not a multiple of 4: odd channels start at 4- or 8-byte alignment (cp.async 4/8-byte prefetch path)."""
+    scene, geo = small
+    mix = synth.mixture(scene, 2, T, seed=13)
+    srp = _native(scene, geo.grids)
+    got = srp.score(torch.from_numpy(mix).cuda(), 24000).cpu().numpy()[0]
+    want = srp_oracle.score(mix, geo.grids, scene.mic_positions, freq_bins, scene.fs, n_fft)
+    assert np.abs(got - want).max() <= TOL * want.max()
+
+
+def test_fs_44100(cuda_device):
+    """BASELINE.json quotes 44.1 kHz; the reference hard-codes 48 kHz.  fs is a parameter here."""
+    scene = synth.small_scene(n_mics=4, seed=6, fs=44100)
+    geo = geometry_oracle.GeometryOracle(scene.mic_positions, scene.roi, FS=44100, build_fine=False)
+    T = 132300
+    mix = synth.mixture(scene, 2, T, seed=3)
+    srp = _native(scene, geo.grids)
+    got = srp.score(torch.from_numpy(mix).cuda(), srp_oracle.window_length(T)).cpu().numpy()[0]
+    want = srp_oracle.score(mix, geo.grids, scene.mic_positions, freq_bins, 44100, n_fft)
+    assert len(srp_oracle.window_starts(T, 36000)) == 6
+    assert np.abs(got - want).max() <= TOL * want.max()
