@@ -361,6 +361,13 @@ int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len,
     gp.npad = h->d_npad;
     gp.off = h->d_off;
     gp.fir = h->d_fir;
+    gp.tw1024 = h->d_tw1024;
+    gp.twpost = h->d_twpost;
+    gp.max_int_lags = 0;
+    for (int p = 0; p < h->P; ++p) {
+        const int ni = (h->n_entries[p] - 1) / h->U + 1 + 12;
+        if (ni > gp.max_int_lags) gp.max_int_lags = ni;
+    }
     gp.B = B;
     gp.Nw = Nw;
     gp.NG = NG;

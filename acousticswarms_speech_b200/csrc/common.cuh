@@ -49,7 +49,7 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(
 
 struct StftCcParams {
     const float* mix;      // [B][M][T]
-    float2* cc_part;       // [B][Nw][NG][F][P]
+    float2* cc_part;       // [B][Nw][NG][P][F]  (bin fastest: coalesced for the writer and for gcc.cu)
     const float2* tw1024;  // [1024]  exp(-2 pi i t / 1024)
     const float2* twpost;  // [F]     exp(-2 pi i k / 2048), k = bin0 + f
     int B, M, T, Nw, step, Nf, NG, FG, bin0, F, P;
@@ -61,7 +61,7 @@ int stft_cc_warp_ctas_per_sm(int M);
 int launch_stft_cc_warp(const StftCcParams& p, cudaStream_t s);
 
 struct GccParams {
-    const float2* cc_part;  // [B][Nw][NG][F][P]
+    const float2* cc_part;  // [B][Nw][NG][P][F]
     float* gcc;             // [B][tab_len * Nw]  pair-major: pair p at Nw*off[p], then [Nw][npad[p]]
     float2* cc_out;         // optional [B][Nw][F][P] summed + 1/Nf scaled (parity tap), may be null
     const int* lag_lo;      // [P] first lag (integer samples) of pair p's table
@@ -69,6 +69,9 @@ struct GccParams {
     const int* npad;        // [P] entries padded to a multiple of 4
     const int* off;         // [P] float offset of the pair segment (per window unit)
     const float* fir;       // [(U-1)][12] Lagrange upsampling weights, nodes -5..+6, fraction fr/U
+    const float2* tw1024;   // [1024] forward twiddles (FFT path), may be null
+    const float2* twpost;   // [F]    exp(-i pi k / 1024), k = bin0 + f (FFT path), may be null
+    int max_int_lags;       // largest integer-lag count (n_int) over the pairs
     int B, Nw, NG, F, P, bin0, U, tab_len;
     float inv_nf, scale;    // 1/Nf ; 1/(F*P)
 };

@@ -1,0 +1,74 @@
+// fft32.cuh -- 32-point register-resident DFT used by the warp-per-FFT kernels (stft_cc_warp.cu, gcc.cu).
+// A 1024-point complex FFT is two of these around one shared-memory transpose: lane t holds z[32 q + t],
+// DFT over q, twiddle by W_1024^{t k1}, transpose, DFT over t; lane k1 then owns Z[k1 + 32 k2].
+#pragma once
+#include "common.cuh"
+
+namespace asw {
+
+__device__ __forceinline__ constexpr int bitrev5(int x) {
+    return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
+}
+
+// cos(2 pi j / 32), sin(2 pi j / 32), j = 0..15
+__device__ constexpr float kC32[16] = {1.0f,           0.98078528040f, 0.92387953251f, 0.83146961230f,
+                                       0.70710678119f, 0.55557023302f, 0.38268343237f, 0.19509032202f,
+                                       0.0f,           -0.19509032202f, -0.38268343237f, -0.55557023302f,
+                                       -0.70710678119f, -0.83146961230f, -0.92387953251f, -0.98078528040f};
+__device__ constexpr float kS32[16] = {0.0f,           0.19509032202f, 0.38268343237f, 0.55557023302f,
+                                       0.70710678119f, 0.83146961230f, 0.92387953251f, 0.98078528040f,
+                                       1.0f,           0.98078528040f, 0.92387953251f, 0.83146961230f,
+                                       0.70710678119f, 0.55557023302f, 0.38268343237f, 0.19509032202f};
+
+// Forward DFT of 32 register-resident points, radix-2 decimation in frequency, fully unrolled.
+// Output X[k] is left at v[bitrev5(k)].
+__device__ __forceinline__ void dft32(float2 (&v)[32]) {
+#pragma unroll
+    for (int len = 32; len >= 2; len >>= 1) {
+        const int half = len >> 1;
+        const int tstep = 32 / len;  // W_len^j = W_32^{j * tstep}
+#pragma unroll
+        for (int blk = 0; blk < 32; blk += len) {
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+                const float2 a = v[blk + j], b = v[blk + j + half];
+                v[blk + j] = make_float2(a.x + b.x, a.y + b.y);
+                const float dx = a.x - b.x, dy = a.y - b.y;
+                const int tw = j * tstep;  // compile-time after unrolling
+                if (tw == 0) {
+                    v[blk + j + half] = make_float2(dx, dy);
+                } else if (tw == 8) {  // multiply by -i
+                    v[blk + j + half] = make_float2(dy, -dx);
+                } else {
+                    const float c = kC32[tw], s = kS32[tw];  // exp(-i theta) = c - i s
+                    v[blk + j + half] = make_float2(fmaf(dx, c, dy * s), fmaf(dy, c, -dx * s));
+                }
+            }
+        }
+    }
+}
+
+// Pass-1 epilogue shared by both users: twiddle Y[k1] (held at v[bitrev5(k1)]) by W_1024^{lane * k1}
+// (seeded exactly every 8 steps from the table) and store transposed into the per-warp tile
+// (re[32][33], im[32][33]: conflict-free both ways).
+__device__ __forceinline__ void twiddle_and_transpose(const float2 (&v)[32], float* tile, int lane, float2 w1, float2 w8,
+                                                      float2 w16, float2 w24) {
+    float2 tw = make_float2(1.f, 0.f);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) {
+        if (k1 == 8) tw = w8;
+        if (k1 == 16) tw = w16;
+        if (k1 == 24) tw = w24;
+        const float2 y = (k1 == 0) ? v[0] : cmul(v[bitrev5(k1)], tw);
+        tile[k1 * 33 + lane] = y.x;
+        tile[32 * 33 + k1 * 33 + lane] = y.y;
+        if ((k1 & 7) != 7) tw = cmul(tw, w1);
+    }
+}
+
+__device__ __forceinline__ void load_transposed(float2 (&v)[32], const float* tile, int lane) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) v[t] = make_float2(tile[lane * 33 + t], tile[32 * 33 + lane * 33 + t]);
+}
+
+}  // namespace asw

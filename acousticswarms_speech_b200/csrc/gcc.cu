@@ -17,6 +17,7 @@
 //      measured) is the same as evaluating every fractional lag directly, at 1/U of the work -- ncu
 //      showed the direct version 87 % issue-bound.
 #include "common.cuh"
+#include "fft32.cuh"
 
 namespace asw {
 namespace {
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(kThreads) gcc_kernel(GccParams p) {
     for (int f = tid; f < Fpad; f += kThreads) {
         float2 s = make_float2(0.f, 0.f);
         if (f < F) {
-            const float2* src = p.cc_part + ((((size_t)b * p.Nw + w) * p.NG) * (size_t)F + f) * p.P + pr;
+            const float2* src = p.cc_part + ((((size_t)b * p.Nw + w) * p.NG) * (size_t)p.P + pr) * F + f;
             for (int g = 0; g < p.NG; ++g) {
                 const float2 v = src[(size_t)g * F * p.P];
                 s.x += v.x;
@@ -108,6 +109,109 @@ __global__ void __launch_bounds__(kThreads) gcc_kernel(GccParams p) {
     }
 }
 
+// Stage A by FFT (one warp per curve): the integer lags of R_p are the inverse real FFT of length 2048 of the
+// one-sided spectrum CC[:, p].  Packed as the usual two-for-one trick run backwards,
+//     Z[k] = (X[k] (1 + i t_k) + conj(X[N-k]) (1 + i conj(t_{N-k}))) / 2,   t_k = exp(i pi k / 1024),  N = 1024,
+//     z = IDFT_N(Z) = conj(DFT_N(conj Z)),   r[2n] = Re z[n],   r[2n+1] = Im z[n],
+// so the warp-FFT of stft_cc_warp.cu (two register DFT-32 passes around one shared transpose) does the work:
+// ~2 k warp-instructions per curve instead of ~16 k for the Horner evaluation of every lag (ncu: the Horner
+// version was 87 % issue-bound).  R_p is periodic in 2048 samples, so lags index the result modulo 2048.
+constexpr int kFftWarps = 4;
+constexpr int kTileFloats = 2 * 32 * 33;
+
+__global__ void __launch_bounds__(32 * kFftWarps) gcc_fft_kernel(GccParams p) {
+    extern __shared__ __align__(16) float s_dyn[];
+    __shared__ float s_fir[7 * kTaps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = s_dyn + warp * (kTileFloats + 2 * kMaxBins);
+    float2* s_x = reinterpret_cast<float2*>(tile + kTileFloats);          // [F] spectrum of this curve
+    const int pr = blockIdx.x * kFftWarps + warp, w = blockIdx.y, b = blockIdx.z;
+    const int F = p.F, U = p.U;
+    for (int i = threadIdx.x; i < (U - 1) * kTaps; i += blockDim.x) s_fir[i] = p.fir[i];
+    __syncthreads();
+    if (pr >= p.P) return;                                               // whole warp exits together
+
+    for (int f = lane; f < F; f += 32) {
+        const float2* src = p.cc_part + ((((size_t)b * p.Nw + w) * p.NG) * (size_t)p.P + pr) * F + f;
+        float2 s = make_float2(0.f, 0.f);
+        for (int g = 0; g < p.NG; ++g) {
+            const float2 v = src[(size_t)g * F * p.P];
+            s.x += v.x;
+            s.y += v.y;
+        }
+        s.x *= p.inv_nf;
+        s.y *= p.inv_nf;
+        if (p.cc_out) p.cc_out[(((size_t)b * p.Nw + w) * F + f) * p.P + pr] = s;
+        s_x[f] = s;
+    }
+    __syncwarp();
+
+    // v[q] = conj(Z[32 q + lane])
+    float2 v[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+        const int k = 32 * q + lane;
+        float2 z = make_float2(0.f, 0.f);
+        const int f1 = k - p.bin0;
+        if (f1 >= 0 && f1 < F) {                                         // X[k] (1 + i t_k) / 2,  t_k = conj(twpost)
+            const float2 x = s_x[f1], t = __ldg(p.twpost + f1);          // twpost = exp(-i pi k / 1024)
+            const float2 m = make_float2(1.f + t.y, t.x);                // 1 + i conj(twpost) = (1 + sin, cos)... see below
+            z = cadd(z, cmul(x, m));
+        }
+        const int kk = (kNc - k) & (kNc - 1);
+        const int f2 = kk - p.bin0;
+        if (f2 >= 0 && f2 < F && k != 0) {                               // conj(X[N-k]) (1 + i conj(t_{N-k})) / 2
+            const float2 x = s_x[f2], t = __ldg(p.twpost + f2);
+            const float2 xc = make_float2(x.x, -x.y);
+            const float2 m = make_float2(1.f - t.y, t.x);                // 1 + i twpost
+            z = cadd(z, cmul(xc, m));
+        }
+        v[q] = make_float2(0.5f * z.x, -0.5f * z.y);
+    }
+    const float2 w1 = __ldg(p.tw1024 + lane);
+    const float2 w8 = __ldg(p.tw1024 + ((8 * lane) & 1023));
+    const float2 w16 = __ldg(p.tw1024 + ((16 * lane) & 1023));
+    const float2 w24 = __ldg(p.tw1024 + ((24 * lane) & 1023));
+    dft32(v);
+    twiddle_and_transpose(v, tile, lane, w1, w8, w16, w24);
+    __syncwarp();
+    load_transposed(v, tile, lane);
+    __syncwarp();
+    dft32(v);   // DFT(conj Z)[lane + 32 k2] at v[bitrev5(k2)];  z[n] = conj of it
+
+    const int lo = p.lag_lo[pr], n = p.n_entries[pr], npd = p.npad[pr];
+    const int n_int = (n - 1) / U + 1 + kTaps;                           // integer lags lo - kMargin ... (<= 2048 here)
+    float* s_r1 = tile;                                                  // the tile is free again
+    const int base = lo - kMargin;
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) {
+        const float2 o = v[bitrev5(k2)];
+        const int l0 = 2 * (lane + 32 * k2);                             // lag of Re z[n]; Im z[n] is lag l0 + 1
+        int j = (l0 - base) & (kNfft - 1);                               // R_p has period 2048
+        if (j < n_int) s_r1[j] = o.x * p.scale;
+        j = (l0 + 1 - base) & (kNfft - 1);
+        if (j < n_int) s_r1[j] = -o.y * p.scale;
+    }
+    __syncwarp();
+
+    float* out = p.gcc + (size_t)b * p.tab_len * p.Nw + (size_t)p.Nw * p.off[pr] + (size_t)w * npd;
+    for (int i = lane; i < npd; i += 32) {
+        float val = 0.f;
+        if (i < n) {
+            const int j = i / U, fr = i - j * U;
+            const float* r = s_r1 + j;
+            if (fr == 0) {
+                val = r[kMargin];
+            } else {
+                const float* wt = s_fir + (fr - 1) * kTaps;
+#pragma unroll
+                for (int t = 0; t < kTaps; ++t) val = fmaf(wt[t], r[t], val);
+            }
+        }
+        out[i] = val;
+    }
+}
+
 }  // namespace
 
 int launch_gcc(const GccParams& p, cudaStream_t s) {
@@ -118,6 +222,19 @@ int launch_gcc(const GccParams& p, cudaStream_t s) {
     if (p.U < 1 || p.U > 8) {
         set_error("gcc: oversampling %d unsupported", p.U);
         return ASW_ERR_ARG;
+    }
+    // FFT path: every pair's integer-lag range must fit one period and the transpose tile
+    if (p.tw1024 && p.twpost && p.max_int_lags <= kTileFloats && p.max_int_lags <= kNfft && p.bin0 + p.F <= kNc) {
+        dim3 grid((p.P + kFftWarps - 1) / kFftWarps, p.Nw, p.B);
+        const size_t smem = (size_t)kFftWarps * (kTileFloats + 2 * kMaxBins) * sizeof(float);
+        static bool attr_set = false;
+        if (!attr_set) {
+            ASW_CUDA_CHECK(cudaFuncSetAttribute(gcc_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        gcc_fft_kernel<<<grid, 32 * kFftWarps, smem, s>>>(p);
+        ASW_LAUNCH_CHECK("gcc_fft_kernel");
+        return ASW_OK;
     }
     dim3 grid(p.P, p.Nw, p.B);
     gcc_kernel<<<grid, kThreads, 0, s>>>(p);

@@ -16,12 +16,12 @@
 namespace asw {
 namespace {
 
-constexpr int kThreads = 1024;           // 32 warps hide the shared-memory gather latency (ncu: short_scoreboard)
+constexpr int kMaxThreads = 1024;        // 32 warps hide the shared-memory gather latency (ncu: short_scoreboard)
 constexpr int kWc = 8;                    // windows per staging chunk
 constexpr int kSmemBudget = 200 * 1024;   // bytes of GCC table staged at once
 
-template <int GPT>
-__global__ void __launch_bounds__(kThreads, 1) srp_gather_kernel(SrpGatherParams p) {
+template <int GPT, int kThreads>
+__global__ void __launch_bounds__(kThreads, kMaxThreads / kThreads) srp_gather_kernel(SrpGatherParams p) {
     extern __shared__ __align__(16) float s_tab[];
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
@@ -98,17 +98,17 @@ __global__ void __launch_bounds__(kThreads, 1) srp_gather_kernel(SrpGatherParams
     }
 }
 
-template <int GPT>
+template <int GPT, int kThreads>
 int launch_t(const SrpGatherParams& p, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        ASW_CUDA_CHECK(cudaFuncSetAttribute(srp_gather_kernel<GPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            kSmemBudget));
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(srp_gather_kernel<GPT, kThreads>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         attr_set = true;
     }
     const int tile = kThreads * GPT;
     dim3 grid((p.G + tile - 1) / tile, p.B);
-    srp_gather_kernel<GPT><<<grid, kThreads, p.smem_bytes, s>>>(p);
+    srp_gather_kernel<GPT, kThreads><<<grid, kThreads, p.smem_bytes, s>>>(p);
     ASW_LAUNCH_CHECK("srp_gather_kernel");
     return ASW_OK;
 }
@@ -124,9 +124,9 @@ int launch_srp_gather(const SrpGatherParams& p, cudaStream_t s) {
         return ASW_ERR_RANGE;
     }
     // Larger tiles amortise the table staging; smaller tiles fill the 148 SMs when the batch is small.
-    const long long tiles2 = (long long)((p.G + kThreads * 2 - 1) / (kThreads * 2)) * p.B;
-    if (tiles2 >= kNumSms) return launch_t<2>(p, s);
-    return launch_t<1>(p, s);
+    const long long tiles2 = (long long)((p.G + kMaxThreads * 2 - 1) / (kMaxThreads * 2)) * p.B;
+    if (tiles2 >= kNumSms) return launch_t<2, kMaxThreads>(p, s);
+    return launch_t<1, kMaxThreads>(p, s);
 }
 
 }  // namespace asw

@@ -8,7 +8,7 @@
 //   :421-426  CC[k, (i,j)] = (1/Nf) sum_n pX[i,k,n] conj(pX[j,k,n]),  i<j row-major, k in [bin0, bin1)
 // Only the scored bins are ever formed.  One CTA owns one (mixture, window, frame group) and all M
 // mics of it: the per-frame pX tile lives in shared memory, the pair sums live in registers (M <= 8)
-// and are written once per CTA as a partial sum cc_part[b][w][group][f][p]; the 1/Nf scaling and
+// and are written once per CTA as a partial sum cc_part[b][w][group][p][f]; the 1/Nf scaling and
 // the sum over groups are folded into the consumer (gcc.cu), so the result is deterministic.
 #include "common.cuh"
 
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kThreads) stft_cc_kernel(StftCcParams p) {
                     for (int jj = i + 1; jj < M; ++jj) {
                         const float2 aj = s_px[jj * F + j];
                         float2 c = make_float2(fmaf(ai.x, aj.x, ai.y * aj.y), fmaf(ai.y, aj.x, -ai.x * aj.y));
-                        float2* dst = cc_out + (size_t)j * p.P + q;
+                        float2* dst = cc_out + (size_t)q * F + j;
                         if (n > n0) {
                             const float2 old = *dst;
                             c.x += old.x;
@@ -153,10 +153,10 @@ __global__ void __launch_bounds__(kThreads) stft_cc_kernel(StftCcParams p) {
     }
     if (MT > 0 && j < F) {
 #pragma unroll
-        for (int q = 0; q < PT; ++q) cc_out[(size_t)j * p.P + q] = acc[q];
+        for (int q = 0; q < PT; ++q) cc_out[(size_t)q * F + j] = acc[q];
     }
     if (MT == 0 && n1 <= n0 && j < F) {
-        for (int q = 0; q < p.P; ++q) cc_out[(size_t)j * p.P + q] = make_float2(0.f, 0.f);
+        for (int q = 0; q < p.P; ++q) cc_out[(size_t)q * F + j] = make_float2(0.f, 0.f);
     }
 }
 

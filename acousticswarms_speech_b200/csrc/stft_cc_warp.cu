@@ -17,53 +17,12 @@
 // shared throughput with 60 % of the shared wavefronts being bank-conflict replays; this version moves
 // 8x less data through shared memory per FFT and has no conflicts.
 #include "common.cuh"
+#include "fft32.cuh"
 
 namespace asw {
 namespace {
 
 constexpr int kK2 = 7;  // second-pass outputs kept on each side: bins k1 + 32 k2, k2 < 7  (k < 224)
-
-__device__ __forceinline__ constexpr int bitrev5(int x) {
-    return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
-}
-
-// cos(2 pi j / 32), sin(2 pi j / 32), j = 0..15
-__device__ constexpr float kC32[16] = {1.0f,           0.98078528040f, 0.92387953251f, 0.83146961230f,
-                                       0.70710678119f, 0.55557023302f, 0.38268343237f, 0.19509032202f,
-                                       0.0f,           -0.19509032202f, -0.38268343237f, -0.55557023302f,
-                                       -0.70710678119f, -0.83146961230f, -0.92387953251f, -0.98078528040f};
-__device__ constexpr float kS32[16] = {0.0f,           0.19509032202f, 0.38268343237f, 0.55557023302f,
-                                       0.70710678119f, 0.83146961230f, 0.92387953251f, 0.98078528040f,
-                                       1.0f,           0.98078528040f, 0.92387953251f, 0.83146961230f,
-                                       0.70710678119f, 0.55557023302f, 0.38268343237f, 0.19509032202f};
-
-// Forward DFT of 32 register-resident points, radix-2 decimation in frequency, fully unrolled.
-// Output X[k] is left at v[bitrev5(k)].
-__device__ __forceinline__ void dft32(float2 (&v)[32]) {
-#pragma unroll
-    for (int len = 32; len >= 2; len >>= 1) {
-        const int half = len >> 1;
-        const int tstep = 32 / len;  // W_len^j = W_32^{j * tstep}
-#pragma unroll
-        for (int blk = 0; blk < 32; blk += len) {
-#pragma unroll
-            for (int j = 0; j < half; ++j) {
-                const float2 a = v[blk + j], b = v[blk + j + half];
-                v[blk + j] = make_float2(a.x + b.x, a.y + b.y);
-                const float dx = a.x - b.x, dy = a.y - b.y;
-                const int tw = j * tstep;  // compile-time after unrolling
-                if (tw == 0) {
-                    v[blk + j + half] = make_float2(dx, dy);
-                } else if (tw == 8) {  // multiply by -i
-                    v[blk + j + half] = make_float2(dy, -dx);
-                } else {
-                    const float c = kC32[tw], s = kS32[tw];  // exp(-i theta) = c - i s
-                    v[blk + j + half] = make_float2(fmaf(dx, c, dy * s), fmaf(dy, c, -dx * s));
-                }
-            }
-        }
-    }
-}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
@@ -149,21 +108,9 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
             }
             __syncwarp();  // every lane has its raw samples before the tile is overwritten
             dft32(v);  // Y[k1] at v[bitrev5(k1)]
-            // twiddle by W_1024^{t k1} (re-seeded every 8 steps) and store transposed: tile[k1][t]
-            float2 tw = make_float2(1.f, 0.f);
-#pragma unroll
-            for (int k1 = 0; k1 < 32; ++k1) {
-                if (k1 == 8) tw = w8;
-                if (k1 == 16) tw = w16;
-                if (k1 == 24) tw = w24;
-                const float2 y = (k1 == 0) ? v[0] : cmul(v[bitrev5(k1)], tw);
-                tile[k1 * 33 + lane] = y.x;
-                tile[32 * 33 + k1 * 33 + lane] = y.y;
-                if ((k1 & 7) != 7) tw = cmul(tw, w1);
-            }
+            twiddle_and_transpose(v, tile, lane, w1, w8, w16, w24);
             __syncwarp();
-#pragma unroll
-            for (int t = 0; t < 32; ++t) v[t] = make_float2(tile[lane * 33 + t], tile[32 * 33 + lane * 33 + t]);
+            load_transposed(v, tile, lane);
             __syncwarp();  // the tile is free again: start fetching the next frame into it
             if (n + 1 < n1) prefetch_frame(tile, xm + (size_t)(n + 1) * kHop, lane);
             dft32(v);      // Z[k1 + 32 k2] at v[bitrev5(k2)], k1 = lane
@@ -219,7 +166,7 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
         const int f = tid + i * C::kThreads;
         if (f < F) {
 #pragma unroll
-            for (int q = 0; q < C::kP; ++q) cc_out[(size_t)f * p.P + q] = acc[i][q];
+            for (int q = 0; q < C::kP; ++q) cc_out[(size_t)q * F + f] = acc[i][q];   // [pair][bin]: coalesced
         }
     }
 }
