@@ -39,6 +39,9 @@ struct asw_select {
     double* d_yy5 = nullptr;      // [Ny5]
     double* d_off1 = nullptr;     // [Ny1][Nx1][Nz][D]
     unsigned char* d_box = nullptr;  // [G] is the untrimmed box of cluster g non-empty
+    // subdivision workspace (grown on demand): per candidate one area list and two ping-pong node lists
+    int32_t* d_lists = nullptr;
+    size_t lists_cap = 0;
 };
 
 namespace asw {
@@ -85,11 +88,9 @@ struct ProbeShared {
     ProbeFlags f;
 };
 
-// "Does the closed TDoA box [lo, hi] contain a 1 cm voxel of the room?" -- hyperbola_area_init (:41-61) reduced to
-// its decision: 5 cm probe over the bucket rows the box touches, the coinciding 1 cm voxels first, the exact 1 cm
-// cut only if none of them is inside.  Block-wide (all threads call it, contains barriers); lo/hi are in shared
-// memory and already visible.  Returns 1 = non-empty, 0 = empty / no 5 cm voxel.
-__device__ int area_nonempty(const SelectParams& p, const double* s_lo, const double* s_hi, ProbeShared* ps) {
+// 5 cm probe (:45-47): counts the 5 cm voxels inside the closed box [lo, hi], their index bounding box, and
+// whether one of the coinciding 1 cm voxels is inside.  Block-wide, ends with a barrier; results in ps->f.
+__device__ void probe5cm(const SelectParams& p, const double* s_lo, const double* s_hi, ProbeShared* ps) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = p.D;
     ProbeFlags* f = &ps->f;
@@ -177,23 +178,39 @@ __device__ int area_nonempty(const SelectParams& p, const double* s_lo, const do
         }
     }
     __syncthreads();
+}
+
+// The reference's 1 cm cut (:49-58): bounding box of the 5 cm hits +- 5 cm, clamped to the room, as index ranges
+// into the 1 cm volume (python slice semantics).  One thread.
+__device__ void cut_box(const SelectParams& p, ProbeShared* ps) {
+    const ProbeFlags* f = &ps->f;
+    double x0 = p.xx5[f->ixmin] - 0.05, x1 = p.xx5[f->ixmax] + 0.05;
+    x0 = fmax(p.ax0, x0);
+    x1 = fmin(p.ax1, x1);
+    double y0 = p.yy5[f->iymin] - 0.05, y1 = p.yy5[f->iymax] + 0.05;
+    y0 = fmax(p.ay0, y0);
+    y1 = fmin(p.ay1, y1);
+    const int ix0 = (int)floor((x0 - p.ax0) / 0.01), ix1 = (int)ceil((x1 - p.ax0) / 0.01);
+    const int iy0 = (int)floor((y0 - p.ay0) / 0.01), iy1 = (int)ceil((y1 - p.ay0) / 0.01);
+    ps->cutbox[0] = max(0, min(ix0, p.Nx1));
+    ps->cutbox[1] = max(0, min(ix1, p.Nx1));
+    ps->cutbox[2] = max(0, min(iy0, p.Ny1));
+    ps->cutbox[3] = max(0, min(iy1, p.Ny1));
+}
+
+// "Does the closed TDoA box [lo, hi] contain a 1 cm voxel of the room?" -- hyperbola_area_init (:41-61) reduced to
+// its decision: 5 cm probe, the coinciding 1 cm voxels first, the exact 1 cm cut only if none of them is inside.
+// Block-wide (all threads call it, contains barriers); lo/hi are in shared memory and already visible.
+// Returns 1 = non-empty, 0 = empty / no 5 cm voxel.
+__device__ int area_nonempty(const SelectParams& p, const double* s_lo, const double* s_hi, ProbeShared* ps) {
+    const int tid = threadIdx.x;
+    const int D = p.D;
+    ProbeFlags* f = &ps->f;
+    probe5cm(p, s_lo, s_hi, ps);
     if (f->cnt5 == 0) return 0;                               // init_area is None (:46-47)
     if (f->hit1 != 0) return 1;
     // exact scan of the reference's 1 cm cut (:49-60); rare: no coinciding 1 cm voxel was inside
-    if (tid == 0) {
-        double x0 = p.xx5[f->ixmin] - 0.05, x1 = p.xx5[f->ixmax] + 0.05;
-        x0 = fmax(p.ax0, x0);
-        x1 = fmin(p.ax1, x1);
-        double y0 = p.yy5[f->iymin] - 0.05, y1 = p.yy5[f->iymax] + 0.05;
-        y0 = fmax(p.ay0, y0);
-        y1 = fmin(p.ay1, y1);
-        const int ix0 = (int)floor((x0 - p.ax0) / 0.01), ix1 = (int)ceil((x1 - p.ax0) / 0.01);
-        const int iy0 = (int)floor((y0 - p.ay0) / 0.01), iy1 = (int)ceil((y1 - p.ay0) / 0.01);
-        ps->cutbox[0] = max(0, min(ix0, p.Nx1));
-        ps->cutbox[1] = max(0, min(ix1, p.Nx1));
-        ps->cutbox[2] = max(0, min(iy0, p.Ny1));
-        ps->cutbox[3] = max(0, min(iy1, p.Ny1));
-    }
+    if (tid == 0) cut_box(p, ps);
     __syncthreads();
     const int ix0 = ps->cutbox[0], nx = ps->cutbox[1] - ix0, iy0 = ps->cutbox[2], ny = ps->cutbox[3] - iy0;
     const long long total = (nx > 0 && ny > 0) ? (long long)nx * ny * p.Nz : 0;
@@ -358,6 +375,331 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(SelectParams p) {
     if (tid == 0) p.out_count[b] = npatch;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Subdivision of the kept coarse hypercubes: search_area / binary_area_divide_width
+// (sep/helpers/local_utils_3d.py:212-335) with Patch.check_out (sep/Traditional_SP/Patch_3D.py:69-87).
+// The reference recomputes the TDoA vector of every 1 cm member point (:220-224); those values are bit for bit
+// Offset_1 at the member voxels (numpy's x ** 0.5 is sqrt), so the device works on voxel indices into Offset_1.
+// A node's member set is always "root members inside an axis-aligned box" (the intersection of the closed
+// half-boxes on the path), which is also what the host needs to rebuild a leaf's area_points on demand.
+constexpr int kSubD = 8;            // TDoA dimensions supported on the device path (M <= 9)
+constexpr int kSubThreads = 256;
+constexpr int kMaxNodes = 128;      // nodes per level
+constexpr int kListCap = 1 << 17;   // member voxels per candidate (and per level, duplicates included)
+
+struct SubNode {
+    int c[kSubD], w[kSubD];
+    double lo[kSubD], hi[kSubD];    // membership box relative to the root's members
+    int start, count;
+};
+
+struct SubParams {
+    SelectParams g;                 // geometry
+    const int32_t* centres;         // [n][D]
+    const int32_t* widths;          // [n] coarse width (identical in every dimension)
+    double ub[kSubD];               // upper_bound_pairwise (sep/Mic_Array.py:113-115)
+    int32_t* lists;                 // [n][3][kListCap]: area list, ping, pong
+    int max_leaves;
+    int32_t* leaf_count;            // [n]
+    int32_t* leaf_off;              // [n][max_leaves][D]
+    int32_t* leaf_w;                // [n][max_leaves][D]
+    int32_t* leaf_npts;             // [n][max_leaves]
+    double* leaf_box;               // [n][max_leaves][2][D]
+    int32_t* root_after;            // [n][2][D] root offsets / widths after check_out (the reference mutates the candidate)
+    int32_t* status;                // [n] 0 ok, 1 member list overflow, 2 node overflow, 3 leaf overflow
+};
+
+__device__ __forceinline__ long long trunc_ll(double x) { return (long long)x; }   // numpy float -> int64 item assignment
+
+__global__ void __launch_bounds__(kSubThreads) subdivide_kernel(SubParams q) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    SubNode* cur = reinterpret_cast<SubNode*>(s_raw);
+    SubNode* nxt = cur + kMaxNodes;
+    __shared__ double s_lo[kMaxD], s_hi[kMaxD];
+    __shared__ ProbeShared ps;
+    __shared__ int s_n, s_cnt[kSubD][2], s_pos[2], s_flag[4];
+    __shared__ double s_blo[kSubD], s_bhi[kSubD], s_hlo[kSubD][2], s_hhi[kSubD][2];
+    __shared__ int s_elig[kSubD], s_hc[kSubD][2], s_hw[kSubD];
+    const SelectParams& p = q.g;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cand = blockIdx.x, D = p.D;
+    int32_t* area = q.lists + (size_t)cand * 3 * kListCap;
+    int32_t* buf[2] = {area + kListCap, area + 2 * kListCap};
+    const int wc = q.widths[cand];
+
+    // ---- member voxels of the coarse patch: hyperbola_area_init (SRP_Prunning.py:41-61), unordered
+    if (tid < D) {
+        const double half = ((double)wc + 0.2) / 2.0;
+        const int c = q.centres[(size_t)cand * D + tid];
+        s_lo[tid] = (double)c - half;
+        s_hi[tid] = (double)c + half;
+    }
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    probe5cm(p, s_lo, s_hi, &ps);
+    int status = 0;
+    if (ps.f.cnt5 > 0) {
+        if (tid == 0) cut_box(p, &ps);
+        __syncthreads();
+        const int ix0 = ps.cutbox[0], nx = ps.cutbox[1] - ix0, iy0 = ps.cutbox[2], ny = ps.cutbox[3] - iy0;
+        const long long total = (nx > 0 && ny > 0) ? (long long)nx * ny * p.Nz : 0;
+        for (long long k0 = 0; k0 < total; k0 += kSubThreads) {
+            const long long k = k0 + tid;
+            bool in = false;
+            int vox = 0;
+            if (k < total) {
+                const int iz = (int)(k % p.Nz);
+                const long long r2 = k / p.Nz;
+                const int ix = ix0 + (int)(r2 % nx), iy = iy0 + (int)(r2 / nx);
+                vox = (iy * p.Nx1 + ix) * p.Nz + iz;
+                const double* o = p.off1 + (size_t)vox * D;
+                in = true;
+                for (int i = 0; i < D; ++i) in = in && (o[i] >= s_lo[i]) && (o[i] <= s_hi[i]);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            int base = 0;
+            if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (in) {
+                const int pos = base + __popc(m & ((1u << lane) - 1));
+                if (pos < kListCap) area[pos] = vox;
+            }
+        }
+    }
+    __syncthreads();
+    int n_root = s_n;
+    if (n_root > kListCap) {
+        n_root = kListCap;
+        status = 1;
+    }
+
+    // ---- level-synchronous walk of the split tree
+    int n_cur = 1, n_leaf = 0;
+    if (tid == 0) {
+        for (int i = 0; i < D; ++i) {
+            cur[0].c[i] = q.centres[(size_t)cand * D + i];
+            cur[0].w[i] = wc;
+            cur[0].lo[i] = s_lo[i];
+            cur[0].hi[i] = s_hi[i];
+        }
+        cur[0].start = 0;
+        cur[0].count = n_root;
+    }
+    __syncthreads();
+    const int32_t* src = area;
+    int level = 0;
+    while (n_cur > 0) {
+        int32_t* dst = buf[level & 1];
+        int n_nxt = 0, dst_off = 0;
+        for (int ni = 0; ni < n_cur; ++ni) {
+            SubNode* nd = &cur[ni];
+            if (tid == 0) {
+                // Patch.check_out (Patch_3D.py:69-87), in place
+                for (int i = 0; i < D; ++i) {
+                    while (true) {
+                        const int c = nd->c[i], w = nd->w[i];
+                        if (fabs((double)c) <= q.ub[i] || w <= 4) break;
+                        if ((double)c > q.ub[i]) nd->c[i] = (int)trunc_ll((double)c - (double)w / 4.0);
+                        else if ((double)c < -q.ub[i]) nd->c[i] = (int)trunc_ll((double)c + (double)w / 4.0);
+                        nd->w[i] = (int)trunc_ll((double)w / 2.0);
+                    }
+                }
+                if (level == 0)
+                    for (int i = 0; i < D; ++i) {
+                        q.root_after[((size_t)cand * 2 + 0) * D + i] = nd->c[i];
+                        q.root_after[((size_t)cand * 2 + 1) * D + i] = nd->w[i];
+                    }
+                int wmax = 0;
+                for (int i = 0; i < D; ++i) wmax = max(wmax, nd->w[i]);
+                // (:260-262) leaf: every dimension fine enough and few enough member points
+                s_flag[0] = ((double)wmax / 2.0 <= 2.0 && nd->count <= 400) ? 1 : 0;
+                for (int i = 0; i < D; ++i) {
+                    const double c = (double)nd->c[i], w = (double)nd->w[i];
+                    s_blo[i] = c - w / 2.0 - 1e-3;            // Patch.hyperbola_sample bounds (Patch_3D.py:40-47)
+                    s_bhi[i] = c + w / 2.0 + 1e-3;
+                    s_elig[i] = (w / 2.0 < 3.0) ? 0 : 1;      // (:271-272) MIN_WIDTH
+                    const int hw = (int)trunc_ll(w / 2.0);    // (:279-280) float into int64
+                    s_hw[i] = hw;
+                    s_hc[i][0] = (int)trunc_ll(c - w / 4.0);  // (:275-278)
+                    s_hc[i][1] = (int)trunc_ll(c + w / 4.0);
+                    for (int sd = 0; sd < 2; ++sd) {
+                        s_hlo[i][sd] = (double)s_hc[i][sd] - (double)hw / 2.0 - 1e-3;
+                        s_hhi[i][sd] = (double)s_hc[i][sd] + (double)hw / 2.0 + 1e-3;
+                    }
+                    s_cnt[i][0] = 0;
+                    s_cnt[i][1] = 0;
+                }
+            }
+            __syncthreads();
+            bool leaf = s_flag[0] != 0;
+            int chosen = -1;
+            if (!leaf) {
+                // one pass: member counts of both halves along every eligible dimension
+                int cnt[kSubD][2];
+#pragma unroll
+                for (int i = 0; i < kSubD; ++i) cnt[i][0] = cnt[i][1] = 0;
+                for (int k = tid; k < nd->count; k += kSubThreads) {
+                    const double* o = p.off1 + (size_t)src[nd->start + k] * D;
+                    unsigned in = 0;
+                    double v[kSubD];
+#pragma unroll
+                    for (int i = 0; i < kSubD; ++i)
+                        if (i < D) {
+                            v[i] = o[i];
+                            if (v[i] >= s_blo[i] && v[i] <= s_bhi[i]) in |= 1u << i;
+                        }
+                    const unsigned all = (1u << D) - 1;
+#pragma unroll
+                    for (int i = 0; i < kSubD; ++i)
+                        if (i < D && s_elig[i] && ((in | (1u << i)) == all)) {
+                            if (v[i] >= s_hlo[i][0] && v[i] <= s_hhi[i][0]) ++cnt[i][0];
+                            if (v[i] >= s_hlo[i][1] && v[i] <= s_hhi[i][1]) ++cnt[i][1];
+                        }
+                }
+#pragma unroll
+                for (int i = 0; i < kSubD; ++i)
+                    if (i < D) {
+#pragma unroll
+                        for (int sd = 0; sd < 2; ++sd) {
+                            int c = cnt[i][sd];
+#pragma unroll
+                            for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+                            if (lane == 0 && c) atomicAdd(&s_cnt[i][sd], c);
+                        }
+                    }
+                __syncthreads();
+                if (tid == 0) {
+                    // the reference's choice (:264-331): most balanced split, dimensions still wider than 2 first
+                    int best = -1, best_diff = 2500000, last = -1;
+                    bool keep8 = false;
+                    for (int i = 0; i < D; ++i) {
+                        if (!s_elig[i]) continue;
+                        last = i;
+                        const int diff = abs(s_cnt[i][0] - s_cnt[i][1]);
+                        if (s_hw[i] > 2) {
+                            if (!keep8) {
+                                best_diff = diff;
+                                best = i;
+                                keep8 = true;
+                            } else if (diff < best_diff) {
+                                best_diff = diff;
+                                best = i;
+                            }
+                        } else if (!keep8 && diff < best_diff) {
+                            best_diff = diff;
+                            best = i;
+                        }
+                    }
+                    // (:333-335) "min_patch is None or len(two_patches) == 0" -- two_patches of the LAST dimension tried
+                    if (best < 0 || last < 0 || (s_cnt[last][0] == 0 && s_cnt[last][1] == 0)) s_flag[1] = -1;
+                    else s_flag[1] = best;
+                    s_pos[0] = 0;
+                    s_pos[1] = 0;
+                }
+                __syncthreads();
+                chosen = s_flag[1];
+                if (chosen < 0) leaf = true;
+            }
+            if (leaf) {
+                if (tid == 0) {
+                    if (n_leaf < q.max_leaves) {
+                        const size_t lb = (size_t)cand * q.max_leaves + n_leaf;
+                        for (int i = 0; i < D; ++i) {
+                            q.leaf_off[lb * D + i] = nd->c[i];
+                            q.leaf_w[lb * D + i] = nd->w[i];
+                            q.leaf_box[(lb * 2 + 0) * D + i] = nd->lo[i];
+                            q.leaf_box[(lb * 2 + 1) * D + i] = nd->hi[i];
+                        }
+                        q.leaf_npts[lb] = nd->count;
+                    }
+                }
+                if (n_leaf >= q.max_leaves) status = 3;
+                ++n_leaf;
+                __syncthreads();
+                continue;
+            }
+            // split along `chosen`: children = the non-empty halves, in order; their members by a second pass
+            const int size0 = s_cnt[chosen][0], size1 = s_cnt[chosen][1];
+            const int off0 = dst_off, off1 = dst_off + size0;
+            const int add = (size0 > 0 ? 1 : 0) + (size1 > 0 ? 1 : 0);
+            if (off1 + size1 > kListCap) {
+                status = 1;                                   // uniform: all of these are shared values
+            } else if (n_nxt + add > kMaxNodes) {
+                status = 2;
+            } else {
+                for (int k0 = 0; k0 < nd->count; k0 += kSubThreads) {
+                    const int k = k0 + tid;
+                    bool in0 = false, in1 = false;
+                    int vox = 0;
+                    if (k < nd->count) {
+                        vox = src[nd->start + k];
+                        const double* o = p.off1 + (size_t)vox * D;
+                        bool others = true;
+                        double vi = 0.0;
+                        for (int i = 0; i < D; ++i) {
+                            const double v = o[i];
+                            if (i == chosen) vi = v;
+                            else others = others && (v >= s_blo[i]) && (v <= s_bhi[i]);
+                        }
+                        in0 = others && vi >= s_hlo[chosen][0] && vi <= s_hhi[chosen][0];
+                        in1 = others && vi >= s_hlo[chosen][1] && vi <= s_hhi[chosen][1];
+                    }
+                    // warp-aggregated append (a member within 1e-3 of the split plane goes to both halves)
+                    const unsigned m0 = __ballot_sync(0xffffffffu, in0), m1 = __ballot_sync(0xffffffffu, in1);
+                    int b0 = 0, b1 = 0;
+                    if (lane == 0) {
+                        if (m0) b0 = atomicAdd(&s_pos[0], __popc(m0));
+                        if (m1) b1 = atomicAdd(&s_pos[1], __popc(m1));
+                    }
+                    b0 = __shfl_sync(0xffffffffu, b0, 0);
+                    b1 = __shfl_sync(0xffffffffu, b1, 0);
+                    const unsigned below = (1u << lane) - 1;
+                    if (in0) dst[off0 + b0 + __popc(m0 & below)] = vox;
+                    if (in1) dst[off1 + b1 + __popc(m1 & below)] = vox;
+                }
+                if (tid == 0) {
+                    int slot = n_nxt;
+                    for (int sd = 0; sd < 2; ++sd) {
+                        const int sz = sd == 0 ? size0 : size1;
+                        if (sz == 0) continue;
+                        SubNode* ch = &nxt[slot++];
+                        for (int i = 0; i < D; ++i) {
+                            ch->c[i] = nd->c[i];
+                            ch->w[i] = nd->w[i];
+                            double lo = s_blo[i], hi = s_bhi[i];
+                            if (i == chosen) {
+                                ch->c[i] = s_hc[i][sd];
+                                ch->w[i] = s_hw[i];
+                                lo = s_hlo[i][sd];
+                                hi = s_hhi[i][sd];
+                            }
+                            ch->lo[i] = fmax(nd->lo[i], lo);
+                            ch->hi[i] = fmin(nd->hi[i], hi);
+                        }
+                        ch->start = sd == 0 ? off0 : off1;
+                        ch->count = sz;
+                    }
+                }
+                n_nxt += add;
+                dst_off = off1 + size1;
+            }
+            __syncthreads();
+        }
+        // next level
+        SubNode* t = cur;
+        cur = nxt;
+        nxt = t;
+        n_cur = n_nxt;
+        src = dst;
+        ++level;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        q.leaf_count[cand] = n_leaf;
+        q.status[cand] = status;
+    }
+}
+
 // Dense shift table from the per-mixture patch lists: shifts[n][0] = 0, shifts[n][c] = offset[c-1]
 // (the offsets are already integers, so round_half_even(float32(.)) of network.py:81-82 is the identity).
 __global__ void build_shift_table_kernel(const int32_t* __restrict__ cnt, const int32_t* __restrict__ off, int B,
@@ -509,6 +851,7 @@ int asw_select_destroy(asw_select_t* h) {
     cudaFree(h->d_yy5);
     cudaFree(h->d_off1);
     cudaFree(h->d_box);
+    cudaFree(h->d_lists);
     delete h;
     return ASW_OK;
 }
@@ -547,6 +890,58 @@ int asw_select_patches(asw_select_t* h, const float* map_dev, const int32_t* pea
     }
     select_kernel<<<B, kSelThreads, smem, (cudaStream_t)stream>>>(p);
     ASW_LAUNCH_CHECK("select_kernel");
+    return ASW_OK;
+}
+
+int asw_subdivide(asw_select_t* h, const int32_t* centres_dev, const int32_t* widths_dev, int n,
+                  const double* upper_bound, int max_leaves, int32_t* leaf_count_dev, int32_t* leaf_off_dev,
+                  int32_t* leaf_w_dev, int32_t* leaf_npts_dev, double* leaf_box_dev, int32_t* root_after_dev,
+                  int32_t* status_dev, void* stream) {
+    if (!h || !centres_dev || !widths_dev || !upper_bound || !leaf_count_dev || !leaf_off_dev || !leaf_w_dev ||
+        !leaf_npts_dev || !leaf_box_dev || !root_after_dev || !status_dev || n < 0 || max_leaves < 1) {
+        set_error("asw_subdivide: null argument or bad shape");
+        return ASW_ERR_ARG;
+    }
+    if (h->D > kSubD) {
+        set_error("asw_subdivide: %d TDoA dimensions exceed the device path's limit of %d (use the host path)", h->D,
+                  kSubD);
+        return ASW_ERR_RANGE;
+    }
+    if (n == 0) return ASW_OK;
+    const size_t need = (size_t)n * 3 * kListCap;
+    if (need > h->lists_cap) {
+        if (h->d_lists) cudaFree(h->d_lists);
+        h->d_lists = nullptr;
+        h->lists_cap = 0;
+        cudaError_t e = cudaMalloc(&h->d_lists, need * sizeof(int32_t));
+        if (e != cudaSuccess) {
+            set_error("asw_subdivide: workspace of %zu bytes: %s", need * sizeof(int32_t), cudaGetErrorString(e));
+            return ASW_ERR_ALLOC;
+        }
+        h->lists_cap = need;
+    }
+    SubParams q{};
+    fill_geometry(h, q.g);
+    q.centres = centres_dev;
+    q.widths = widths_dev;
+    for (int i = 0; i < h->D; ++i) q.ub[i] = upper_bound[i];
+    q.lists = h->d_lists;
+    q.max_leaves = max_leaves;
+    q.leaf_count = leaf_count_dev;
+    q.leaf_off = leaf_off_dev;
+    q.leaf_w = leaf_w_dev;
+    q.leaf_npts = leaf_npts_dev;
+    q.leaf_box = leaf_box_dev;
+    q.root_after = root_after_dev;
+    q.status = status_dev;
+    const size_t smem = 2 * (size_t)kMaxNodes * sizeof(SubNode);
+    static bool attr_set = false;
+    if (!attr_set) {
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(subdivide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    subdivide_kernel<<<n, kSubThreads, smem, (cudaStream_t)stream>>>(q);
+    ASW_LAUNCH_CHECK("subdivide_kernel");
     return ASW_OK;
 }
 

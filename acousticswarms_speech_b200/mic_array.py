@@ -11,7 +11,7 @@ import torch
 
 from .constants import (FS, INIT_WIDTH, SPEED_OF_SOUND, SPOT_POWER_THRESHOLD2, SRP_THRESHOLDS,
                         USE_RELATIVE_SPOT_POWER, freq_bins, n_fft, window_length)
-from .local_utils import binary_search_baseline, max_avg_power, search_area, si_sdr
+from .local_utils import _tdoa_rows, binary_search_baseline, max_avg_power, search_area, si_sdr
 from .patch import Patch
 from .srp_phat import SRP_PHAT
 
@@ -95,14 +95,57 @@ class Mic_Array(object):
         self.Relative_Threshold = Relative_Threshold
         return candidate_finished
 
+    def _search_area_device(self, candidates):
+        """search_area (local_utils_3d.py:212-246) for all candidates in one launch (asw_subdivide).  The
+        candidates are mutated exactly as the reference's check_out does; a leaf's ``area_points`` is rebuilt on
+        first use from the candidate's points and the leaf's TDoA box, in the reference's order."""
+        import torch
+        from . import native
+        node = self.SRP_node
+        D = self.num_mic - 1
+        dev = node.device
+        centres = np.stack([np.asarray(c.sample_offset, dtype=np.int32) for c in candidates])
+        widths = np.array([int(c.width_list[0]) for c in candidates], dtype=np.int32)
+        for c in candidates:
+            if not np.all(np.asarray(c.width_list) == c.width_list[0]):
+                raise native._lib.AswError("coarse patches must have one width in every dimension")
+        cn, off, wid, npts, box, root = native.subdivide(node.native_select, torch.from_numpy(centres).to(dev),
+                                                         torch.from_numpy(widths).to(dev), self.upper_bound_pairwise)
+        out = []
+        for i, cand in enumerate(candidates):
+            root_box_lo = centres[i].astype(np.float64) - (float(widths[i]) + 0.2) / 2
+            untouched = cn[i] == 1 and np.array_equal(box[i, 0, 0], root_box_lo)    # the root itself is the leaf
+            parent_area = cand.area_points
+            cand.sample_offset[:] = root[i, 0]
+            cand.width_list[:] = root[i, 1]
+            if untouched:
+                out.append([cand])
+                continue
+
+            def builder(lo, hi, area=parent_area):
+                def build():
+                    rows = _tdoa_rows(area, self.mic_positions)
+                    keep = np.all((rows >= lo[:, None]) & (rows <= hi[:, None]), axis=0)
+                    return area[:, keep]
+                return build
+
+            out.append([Patch(off[i, l].astype(np.int64), wid[i, l].astype(np.int64), None, None,
+                              area_fn=builder(box[i, l, 0].copy(), box[i, l, 1].copy())) for l in range(int(cn[i]))])
+        return out
+
     def small_patch_list(self, candidate_finished):
         """The patch-list assembly of Spotform_Small_Patch_Parallel (:244-262): fine hypercubes from
         ``search_area`` plus one width-2 centre patch per candidate."""
         width_list0 = [2 for _ in range(self.num_mic - 1)]
         total_patch, patches_indexes, init_area_total, centre_total = [], [0], [], []
         self.spotforming_times = 0
-        for cand in candidate_finished:
-            patch_processed = search_area([cand], self.mic_positions, self.upper_bound_pairwise)
+        on_device = (self.SRP_node.native is not None and self.num_mic - 1 <= 8 and len(candidate_finished) > 0)
+        fine_lists = self._search_area_device(candidate_finished) if on_device else None
+        for ci, cand in enumerate(candidate_finished):
+            if on_device:
+                patch_processed = fine_lists[ci]
+            else:
+                patch_processed = search_area([cand], self.mic_positions, self.upper_bound_pairwise)
             init_area_total.append(cand.area_points)
             patch_center0 = Patch(cand.sample_offset, width_list0, None, cand.peak_pos)
             centre = patch_center0.center_pos()

@@ -242,6 +242,35 @@ class NativeSelect:
         return n, off, wid, pk
 
 
+def subdivide(select_handle, centres, widths, upper_bound, max_leaves=128):
+    """Device search_area for n coarse patches.  centres (n, D) int32 CUDA, widths (n,) int32 CUDA,
+    upper_bound (D,) float64 host.  Returns host numpy arrays
+    (leaf_count (n,), leaf_off (n, L, D), leaf_w (n, L, D), leaf_npts (n, L), leaf_box (n, L, 2, D), root_after (n, 2, D))."""
+    _require_cuda(centres, "centres", torch.int32)
+    _require_cuda(widths, "widths", torch.int32)
+    n, D = centres.shape
+    dev = centres.device
+    ub = np.ascontiguousarray(upper_bound, dtype=np.float64)
+    if ub.shape != (D,):
+        raise _lib.AswError(f"upper_bound must have {D} entries")
+    cnt = torch.zeros((n,), device=dev, dtype=torch.int32)
+    off = torch.zeros((n, max_leaves, D), device=dev, dtype=torch.int32)
+    wid = torch.zeros((n, max_leaves, D), device=dev, dtype=torch.int32)
+    npts = torch.zeros((n, max_leaves), device=dev, dtype=torch.int32)
+    box = torch.zeros((n, max_leaves, 2, D), device=dev, dtype=torch.float64)
+    root = torch.zeros((n, 2, D), device=dev, dtype=torch.int32)
+    status = torch.zeros((n,), device=dev, dtype=torch.int32)
+    if n:
+        _lib.check(select_handle.lib.asw_subdivide(select_handle._h, _ptr(centres), _ptr(widths), n, ub.ctypes.data,
+                                                   int(max_leaves), _ptr(cnt), _ptr(off), _ptr(wid), _ptr(npts),
+                                                   _ptr(box), _ptr(root), _ptr(status), _stream(dev)))
+    st = status.cpu().numpy()
+    cn = cnt.cpu().numpy()
+    if (st != 0).any() or (cn > max_leaves).any():
+        raise _lib.AswError(f"asw_subdivide: capacity exceeded (status {st.tolist()}, leaves {cn.tolist()})")
+    return cn, off.cpu().numpy(), wid.cpu().numpy(), npts.cpu().numpy(), box.cpu().numpy(), root.cpu().numpy()
+
+
 def build_shift_table(n_patches, offsets, capacity, shifts=None, mix_index=None, n_total=None):
     """Per-mixture patch lists -> dense (capacity, D + 1) int32 shift table, (capacity,) mixture index and the
     device-resident total, without leaving the device."""

@@ -187,6 +187,23 @@ int asw_select_patches(asw_select_t* h, const float* map_dev, const int32_t* pea
                        const int32_t* count_dev, int B, int32_t* out_count_dev, int32_t* out_offsets_dev,
                        int32_t* out_width_dev, int32_t* out_peak_dev, int max_patches, void* stream);
 
+/* Subdivision of kept coarse hypercubes into fine ones: search_area / binary_area_divide_width
+ * (sep/helpers/local_utils_3d.py:212-335) with Patch.check_out (sep/Traditional_SP/Patch_3D.py:69-87), one
+ * candidate per CTA.  Needs D <= 8 (M <= 9); larger arrays use the host code.
+ *   centres_dev [n][D] int32, widths_dev [n] int32   the coarse patches (width identical in every dimension)
+ *   upper_bound [D] float64 (host)                    upper_bound_pairwise (sep/Mic_Array.py:113-115)
+ * Outputs per candidate c, leaf l < min(leaf_count[c], max_leaves), in the reference's order:
+ *   leaf_off [n][max_leaves][D], leaf_w [n][max_leaves][D] int32   Patch.sample_offset / width_list
+ *   leaf_npts [n][max_leaves] int32                                area_size()
+ *   leaf_box [n][max_leaves][2][D] float64   closed TDoA box (lo, hi) selecting the leaf's member points among the
+ *                                            candidate's area_points (so the host can rebuild them in order)
+ *   root_after [n][2][D] int32   the candidate's offsets / widths after check_out (the reference mutates it in place)
+ *   status [n] int32             0 ok; 1/2/3 = member-list / node / leaf capacity exceeded (results incomplete) */
+int asw_subdivide(asw_select_t* h, const int32_t* centres_dev, const int32_t* widths_dev, int n,
+                  const double* upper_bound, int max_leaves, int32_t* leaf_count_dev, int32_t* leaf_off_dev,
+                  int32_t* leaf_w_dev, int32_t* leaf_npts_dev, double* leaf_box_dev, int32_t* root_after_dev,
+                  int32_t* status_dev, void* stream);
+
 /* Dense shift table for asw_shift_stack from the per-mixture patch lists above:
  *   shifts_dev [capacity][D+1] int32 (column 0 = 0), mix_index_dev [capacity] int32,
  *   n_total_dev [1] int32 = min(total patches, capacity).  B <= 1024. */

@@ -332,3 +332,39 @@ def test_two_mic_array_end_to_end(cuda_device):
         assert [list(p.width_list) for p in d] == [list(p.width_list) for p in h]
     patches, _ = ma.Apply_SRP_PHAT(torch.from_numpy(mixes[0]))
     assert [list(p.sample_offset) for p in patches] == [list(p.sample_offset) for p in dev_lists[0]]
+
+
+def test_device_subdivision_equals_host(cuda_device, desk):
+    """asw_subdivide vs the host mirror of search_area / binary_area_divide_width / Patch.check_out
+    (local_utils_3d.py:212-335, Patch_3D.py:69-87) on the coarse patches of several mixtures: leaf offsets,
+    widths, member counts and ORDER identical; candidates mutated identically; lazily rebuilt leaf members equal."""
+    import copy
+    from acousticswarms_speech_b200 import local_utils
+    from acousticswarms_speech_b200.pipeline import FrontEnd
+    g, scene, mix, ma = desk
+    node = ma.SRP_node
+    fe = FrontEnd(node)
+    mixes = np.stack([mix, synth.mixture(scene, 5, mix.shape[1], seed=41), synth.mixture(scene, 8, mix.shape[1], seed=42)])
+    lists = fe.prune(fe.score(torch.from_numpy(mixes).cuda())[0])
+    # a tighter physical bound makes check_out fire on some candidates
+    for ub in (ma.upper_bound_pairwise, ma.upper_bound_pairwise * 0.35):
+        saved = ma.upper_bound_pairwise
+        ma.upper_bound_pairwise = ub
+        try:
+            for cands in lists:
+                cands = cands[:12]
+                host_c = copy.deepcopy(cands)
+                for c in host_c:
+                    c.area_points                     # materialise before deepcopy-independent use
+                dev_c = copy.deepcopy(host_c)
+                want = [local_utils.search_area([c], scene.mic_positions, ub) for c in host_c]
+                got = ma._search_area_device(dev_c)
+                for w, gl, hc, dc in zip(want, got, host_c, dev_c):
+                    assert [list(p.sample_offset) for p in gl] == [list(p.sample_offset) for p in w]
+                    assert [list(p.width_list) for p in gl] == [list(p.width_list) for p in w]
+                    assert [p.area_size() for p in gl] == [p.area_size() for p in w]
+                    assert np.array_equal(dc.sample_offset, hc.sample_offset) and np.array_equal(dc.width_list, hc.width_list)
+                    for a, b in list(zip(gl, w))[:3]:
+                        assert np.array_equal(a.area_points, b.area_points)
+        finally:
+            ma.upper_bound_pairwise = saved
