@@ -122,9 +122,13 @@ class Mic_Array(object):
                 out.append([cand])
                 continue
 
-            def builder(lo, hi, area=parent_area):
+            rows_cache = {}
+
+            def builder(lo, hi, area=parent_area, cache=rows_cache):
                 def build():
-                    rows = _tdoa_rows(area, self.mic_positions)
+                    if "rows" not in cache:              # the candidate's TDoA rows, once for all its leaves
+                        cache["rows"] = _tdoa_rows(area, self.mic_positions)
+                    rows = cache["rows"]
                     keep = np.all((rows >= lo[:, None]) & (rows <= hi[:, None]), axis=0)
                     return area[:, keep]
                 return build
