@@ -368,3 +368,59 @@ def test_device_subdivision_equals_host(cuda_device, desk):
                         assert np.array_equal(a.area_points, b.area_points)
         finally:
             ma.upper_bound_pairwise = saved
+
+
+@pytest.mark.parametrize("n_spk,seed,noise", [(5, 101, 1e-3), (8, 102, 1e-2), (0, 103, 1e-3)])
+def test_c2_size_subset_parity(cuda_device, desk, n_spk, seed, noise):
+    """Full C2-size maps (G = 17.7 k) for more scenes -- 5 and 8 speakers, and noise only -- against the oracle's
+    reference contraction on a random subset of hypercubes."""
+    g, scene, mix, ma = desk
+    node = ma.SRP_node
+    x = synth.mixture(scene, n_spk, 144000, seed=seed, noise=noise)
+    got = node.native.score(torch.from_numpy(x).cuda(), 36000)[0].cpu().numpy()
+    rng = np.random.default_rng(seed)
+    sel = np.sort(rng.choice(node.grids.shape[0], 400, replace=False))
+    sel[0] = int(got.argmax())                       # always include the maximum
+    want = np.zeros(len(sel))
+    for s0 in srp_oracle.window_starts(144000, 36000):
+        X = srp_oracle.stft_window(x[:, s0:s0 + 36000], 2048, 512)
+        CC = srp_oracle.cross_spectra(srp_oracle.phat(X), constants.freq_bins)
+        want = np.maximum(want, srp_oracle.contract(CC, node.grids[sel], scene.mic_positions, constants.freq_bins,
+                                                    48000, 2048))
+    assert np.abs(got[sel] - want).max() <= TOL * max(got.max(), 1e-12)
+
+
+def test_capacity_guards(cuda_device, desk):
+    """Device lists that would truncate results must raise, never return silently shortened lists."""
+    from acousticswarms_speech_b200 import _lib, native
+    from acousticswarms_speech_b200.pipeline import FrontEnd
+    g, scene, mix, ma = desk
+    node = ma.SRP_node
+    fe = FrontEnd(node)
+    smap, _, _ = fe.score(torch.from_numpy(mix[None]).cuda())
+    tiny = native.NativePeaks(node.POWER_INDEX, node._member, node.dis_matrix, node.grids.shape[0], node.threshold,
+                              max_peaks=8)
+    peaks, count, mx = tiny.find(smap)
+    assert int(count[0]) == len(g["peaks"]) > 8 and (peaks[0].cpu().numpy() >= 0).all()   # count is exact, list truncated
+    saved = node.native_peaks
+    node.native_peaks = tiny
+    try:
+        with pytest.raises(_lib.AswError):
+            fe.prune(smap)
+        with pytest.raises(_lib.AswError):
+            node.SRP_map = smap[0]
+            node.local_source_adaptive_device()
+    finally:
+        node.native_peaks = saved
+    # shift table capacity: total is clamped and reported, rows beyond it are never written
+    n, off, wid, pk = fe.select(smap)
+    shifts, mi, ntot = fe.shift_table(n, off, 5)
+    assert int(ntot[0]) == 5 and shifts.shape == (5, 7)
+    # counted shift-stack honours n_base: rows [3, 5) are written, slot 2 of the output (row 5 >= n_total) is not
+    out = torch.full((3, 7, mix.shape[1]), -7.0, device="cuda")
+    native.shift_stack_counted(torch.from_numpy(mix[None]).cuda(), shifts, mi, ntot, 3, 3, out)
+    o = out.cpu().numpy()
+    sh = shifts.cpu().numpy()
+    for j in range(2):
+        assert np.array_equal(o[j], shift_oracle.roll_by_gather(mix, -sh[3 + j].astype(np.int64)))
+    assert (o[2] == -7.0).all()
