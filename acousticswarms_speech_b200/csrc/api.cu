@@ -335,7 +335,6 @@ int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len,
     // B mixtures on one GPU and B/n mixtures on each of n GPUs give bit-identical maps.
     const int FG = 8;
     const int NG = (Nf + FG - 1) / FG;
-    (void)fast;
     sp.NG = NG;
     sp.FG = FG;
 
