@@ -217,7 +217,9 @@ def run_b200(args, rank, world):
     count_pin = torch.empty((B,), dtype=torch.int32).pin_memory()
     # the one collective: all ranks' (value, index) top-K lists, packed into a single all-gather per step
     # and issued on a side stream so it overlaps the shift-stack
-    pack = torch.empty((B, 2 * K), device=dev) if world > 1 else None
+    NPACK = 4               # ring: the scoring stream never waits for a collective unless it is 4 steps behind
+    packs = [torch.empty((B, 2 * K), device=dev) for _ in range(NPACK)] if world > 1 else None
+    pack_free = [None] * NPACK
     gathered = torch.empty((world * B, 2 * K), device=dev) if world > 1 else None
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
 
@@ -248,7 +250,10 @@ def run_b200(args, rank, world):
             main.wait_event(map_free[slot])              # prune of step i-2 is done with this map buffer
         m, val, idx = fe.score(src, out=maps[slot])
         if world > 1:          # the one collective of the path: every rank learns every mixture's top-K
-            main.wait_stream(comm_stream)                # previous step's gather has read `pack`
+            ps = (step_no[0] - 1) % NPACK
+            pack = packs[ps]
+            if pack_free[ps] is not None:
+                main.wait_event(pack_free[ps])           # the gather that read this buffer NPACK steps ago
             pack[:, :K] = val
             pack[:, K:] = idx.view(torch.float32)
             packed = torch.cuda.Event()
@@ -256,6 +261,8 @@ def run_b200(args, rank, world):
             comm_stream.wait_event(packed)
             with torch.cuda.stream(comm_stream):
                 dist.all_gather_into_tensor(gathered, pack)
+                pack_free[ps] = torch.cuda.Event()
+                pack_free[ps].record(comm_stream)
         serial = stack_stream is None
         pstream = main if serial else prune_stream
         sstream = main if serial else stack_stream
