@@ -16,7 +16,7 @@ SYMBOLS = [
     "asw_geometry_cluster",
     "asw_peaks_create", "asw_peaks_destroy", "asw_peaks_find",
     "asw_select_create", "asw_select_destroy", "asw_select_patches", "asw_subdivide",
-    "asw_build_shift_table", "asw_shift_stack_counted", "asw_pcm16_to_f32",
+    "asw_build_shift_table", "asw_shift_stack_counted", "asw_pcm16_to_f32", "asw_patch_powers",
 ]
 
 
@@ -65,6 +65,7 @@ def load():
     lib.asw_build_shift_table.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp]
     lib.asw_shift_stack_counted.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
     lib.asw_pcm16_to_f32.argtypes = [vp, vp, c.c_longlong, vp]
+    lib.asw_patch_powers.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name, None)
         if fn is not None and name not in ("asw_last_error", "asw_launch_count"):

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libasw.so")
 STAMP = os.path.join(LIBDIR, "libasw.stamp")
-SOURCES = ["api.cu", "stft_cc.cu", "stft_cc_warp.cu", "gcc.cu", "srp_gather.cu", "topk.cu", "shift_stack.cu", "prune.cu", "select.cu", "geometry.cu"]
+SOURCES = ["api.cu", "stft_cc.cu", "stft_cc_warp.cu", "gcc.cu", "srp_gather.cu", "topk.cu", "shift_stack.cu", "prune.cu", "select.cu", "geometry.cu", "powers.cu"]
 # The warp-FFT kernel needs <= 128 registers/thread so that two CTAs fit the per-partition register files.
 PER_FILE_FLAGS = {"stft_cc_warp.cu": ["-maxrregcount=128"]}
 NVCC_FLAGS = [

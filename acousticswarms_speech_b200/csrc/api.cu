@@ -464,6 +464,16 @@ int asw_pcm16_to_f32(const int16_t* pcm_dev, float* out_dev, long long n, void* 
     return launch_pcm16_to_f32(reinterpret_cast<const short*>(pcm_dev), out_dev, (size_t)n, (cudaStream_t)stream);
 }
 
+int asw_patch_powers(float* x_dev, int N, int T, int window, int demean, float* mean_dev, float* power_dev,
+                     float* maxavg_dev, int32_t* argmax_dev, void* stream) {
+    if (N < 0 || T < 1 || window < 1 || (N > 0 && (!x_dev || !mean_dev || !power_dev || !maxavg_dev))) {
+        set_error("asw_patch_powers: null buffer or bad shape (N=%d T=%d window=%d)", N, T, window);
+        return ASW_ERR_ARG;
+    }
+    return launch_patch_powers(x_dev, N, T, window, demean, mean_dev, power_dev, maxavg_dev, argmax_dev,
+                               (cudaStream_t)stream);
+}
+
 int asw_shift_stack_counted(const float* mix_dev, const int32_t* shifts_dev, const int32_t* mix_index_dev,
                             const int32_t* n_valid_dev, int n_base, int N, int B, int M, int T, float* out_dev,
                             void* stream) {

@@ -76,6 +76,8 @@ struct GccParams {
     float inv_nf, scale;    // 1/Nf ; 1/(F*P)
 };
 int launch_gcc(const GccParams& p, cudaStream_t s);
+int launch_patch_powers(float* x, int N, int T, int W, int demean, float* mean_out, float* power_out,
+                        float* maxavg_out, int* argmax_out, cudaStream_t s);
 
 struct SrpGatherParams {
     const float* gcc;       // as above

@@ -115,11 +115,19 @@ def binary_area_divide_width(patch, samples0, mic_positions, upper_bound_pairwis
 
 def binary_search_baseline(mix_data, spot_model, patch_list, mic_positions):
     """Coarse stage: run the spot model on every coarse hypercube, keep the energetic ones (:339-388)."""
-    sep_data = spot_model.shift_and_sep(mix_data, patch_list, Strict=0)
+    device_powers = getattr(spot_model, "shift_and_sep_powers", None)
+    if device_powers is not None:           # de-mean + max_avg_power of every row in one libasw.so launch
+        sep_data, _, win = device_powers(mix_data, patch_list, Strict=0)
+    else:                                   # a foreign spot model: the reference's per-row host loop
+        sep_data = spot_model.shift_and_sep(mix_data, patch_list, Strict=0)
+        win = None
     powers_win, powers_with_dis = [], []
     for i in range(sep_data.shape[0]):
-        sep_data[i, :] = sep_data[i, :] - np.mean(sep_data[i, :])
-        p, _ = max_avg_power(sep_data[i, :])
+        if win is None:
+            sep_data[i, :] = sep_data[i, :] - np.mean(sep_data[i, :])
+            p, _ = max_avg_power(sep_data[i, :])
+        else:
+            p = win[i]
         powers_win.append(p)
         centre = patch_list[i].center_pos()
         d = np.linalg.norm(centre - mic_positions[0]) if centre.shape[0] == 3 else 4

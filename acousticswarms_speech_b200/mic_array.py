@@ -170,7 +170,12 @@ class Mic_Array(object):
         else:
             thr_new = SPOT_POWER_THRESHOLD2
         total_patch, patches_indexes, init_area_total, centre_total = self.small_patch_list(candidate_finished)
-        sep_data_total = spot_model.shift_and_sep(mix_data, total_patch, Strict=1)
+        device_powers = getattr(spot_model, "shift_and_sep_powers", None)
+        if device_powers is not None:       # rows come back de-meaned, with both powers, from one launch
+            sep_data_total, power_total, power2_total = device_powers(mix_data, total_patch, Strict=1)
+        else:
+            sep_data_total = spot_model.shift_and_sep(mix_data, total_patch, Strict=1)
+            power_total = power2_total = None
 
         for i in range(len(patches_indexes) - 1):
             big_offset = candidate_finished[i].sample_offset
@@ -185,10 +190,14 @@ class Mic_Array(object):
             init_area = init_area_total[i]
             Big_patch_center = centre_total[i]
             powers, powers2 = [], []
-            for j in range(len(patch_processed)):
-                sep_data[j, :] = sep_data[j, :] - np.mean(sep_data[j, :])
-                powers.append(np.sum(sep_data[j, :] ** 2))
-                powers2.append(max_avg_power(sep_data[j, :])[0])
+            if power_total is not None:
+                powers = list(power_total[patches_indexes[i]:patches_indexes[i + 1]])
+                powers2 = list(power2_total[patches_indexes[i]:patches_indexes[i + 1]])
+            else:
+                for j in range(len(patch_processed)):
+                    sep_data[j, :] = sep_data[j, :] - np.mean(sep_data[j, :])
+                    powers.append(np.sum(sep_data[j, :] ** 2))
+                    powers2.append(max_avg_power(sep_data[j, :])[0])
             cpos = candidate_finished[i].center_pos()
             d = np.linalg.norm(cpos - self.mic_positions[0]) if cpos.shape[0] == 3 else 4
             if np.amax(powers2) < thr_new / (1 + d):

@@ -389,6 +389,24 @@ def pcm16_to_f32(pcm, out=None):
     return out
 
 
+def patch_powers(x, window=12000, demean=True):
+    """Per-row statistics of the separator's outputs (local_utils_3d.py:342-349, Mic_Array.py:288-296):
+    ``x`` (N, T) float32 CUDA, de-meaned in place when ``demean`` ->
+    (mean (N,), power = sum((x-mean)^2) (N,), max_avg_power (N,), start of that box (N,) int32)."""
+    _require_cuda(x, "x", torch.float32)
+    if x.dim() != 2:
+        raise _lib.AswError("x must be (N, T)")
+    N, T = x.shape
+    mean = torch.empty((N,), device=x.device, dtype=torch.float32)
+    power = torch.empty((N,), device=x.device, dtype=torch.float32)
+    maxavg = torch.empty((N,), device=x.device, dtype=torch.float32)
+    arg = torch.empty((N,), device=x.device, dtype=torch.int32)
+    if N:
+        _lib.check(_lib.load().asw_patch_powers(_ptr(x), N, T, int(window), int(bool(demean)), _ptr(mean), _ptr(power),
+                                                _ptr(maxavg), _ptr(arg), _stream(x.device)))
+    return mean, power, maxavg, arg
+
+
 def offsets_to_shifts(offsets):
     """Patch.sample_offset list -> (N, M) int32 read offsets: r[0] = 0, r[c] = round_half_even(float32(off[c-1]))
     (sep/training/JointModel/network.py:81-82)."""

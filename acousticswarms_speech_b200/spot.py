@@ -46,8 +46,8 @@ class DataParallelSpotModel(nn.Module):
     def device(self):
         return self._device
 
-    def shift_and_sep(self, input_channels, patch_list, Strict=0, save_input=False):
-        """network.py:37-104 -> np.ndarray (N, T) float32."""
+    def _shift_and_sep_device(self, input_channels, patch_list, Strict, save_input):
+        """network.py:37-101 up to (not including) the copy back: (N, T) results on the device."""
         B = self.batch_size
         N = len(patch_list)
         dev = self.device
@@ -71,7 +71,21 @@ class DataParallelSpotModel(nn.Module):
                     saved.append(unnormalize_input(data_norm, means, stds).cpu())
                 result = self.model(data_norm.to(self.dtype), cond[:n])
                 results[i:i + n] = unnormalize_input(result, means.to(self.dtype), stds.to(self.dtype))[:, 0]
-            out = results.cpu().float().numpy()
+        return results, (torch.cat(saved) if saved else torch.zeros((0, M, T)))
+
+    def shift_and_sep(self, input_channels, patch_list, Strict=0, save_input=False):
+        """network.py:37-104 -> np.ndarray (N, T) float32."""
+        results, saved = self._shift_and_sep_device(input_channels, patch_list, Strict, save_input)
+        out = results.cpu().float().numpy()
         if save_input:
-            return out, (torch.cat(saved) if saved else torch.zeros((0, M, T)))
+            return out, saved
         return out
+
+    def shift_and_sep_powers(self, input_channels, patch_list, Strict=0, window=12000):
+        """``shift_and_sep`` followed, still on the device, by what every caller does next with each row
+        (local_utils_3d.py:342-349, Mic_Array.py:288-296): de-mean in place, ``np.sum(x ** 2)`` and
+        ``max_avg_power(x)[0]``.  -> (de-meaned outputs (N, T) float32 numpy, powers (N,), max_avg_powers (N,))."""
+        results, _ = self._shift_and_sep_device(input_channels, patch_list, Strict, False)
+        x = results.float().contiguous()
+        _, power, maxavg, _ = native.patch_powers(x, window=window, demean=True)
+        return x.cpu().numpy(), power.cpu().numpy(), maxavg.cpu().numpy()

@@ -112,6 +112,19 @@ int asw_map_topk(const float* map_dev, int B, int G, int K, int idx_offset,
 int asw_pcm16_to_f32(const int16_t* pcm_dev, float* out_dev, long long n, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Per-patch statistics of the separator's outputs, the numpy loops of binary_search_baseline
+ * (sep/helpers/local_utils_3d.py:342-349) and Spotform_Small_Patch_Parallel (sep/Mic_Array.py:288-296):
+ *     mean[n]   = mean(x[n])                                      (float32)
+ *     x[n]     -= mean[n]            in place when demean != 0
+ *     power[n]  = sum((x[n] - mean[n])^2)
+ *     maxavg[n] = max_avg_power(x[n] - mean[n], window)[0]        (local_utils_3d.py:13-17: the largest RMS over
+ *                 any `window`-sample box, zeros to the right of the signal), argmax[n] = start of that box
+ * x_dev [N][T] float32; sums are carried in double (numpy / scipy results agree to float32 rounding).
+ * argmax_dev may be NULL. */
+int asw_patch_powers(float* x_dev, int N, int T, int window, int demean, float* mean_dev, float* power_dev,
+                     float* maxavg_dev, int32_t* argmax_dev, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Shift-and-stack: the loop of DataParallelSpotModel.shift_and_sep
  * (sep/training/JointModel/network.py:75-83) with roll_by_gather (:12-25):
  *     out[n][c][t] = mix[mix_index[n]][c][(t + shifts[n][c]) mod T]

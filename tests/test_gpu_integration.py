@@ -309,6 +309,65 @@ def test_spotform_big_and_small_patch_drop_in(cuda_device, desk):
         assert set(offs) == {"audio_offset", "localization_offset"} and label == -1
 
 
+@pytest.mark.parametrize("T,W", [(144000, 12000), (50001, 12000), (9000, 12000), (12000, 12000), (12001, 12000), (700, 64)])
+def test_patch_powers_match_numpy(cuda_device, T, W):
+    """asw_patch_powers vs the numpy / scipy rows of binary_search_baseline (local_utils_3d.py:342-349) and
+    Spotform_Small_Patch_Parallel (Mic_Array.py:288-296)."""
+    from acousticswarms_speech_b200 import native
+    from acousticswarms_speech_b200.local_utils import max_avg_power
+    rng = np.random.default_rng(T)
+    N = 9
+    x = (0.05 * rng.standard_normal((N, T))).astype(np.float32)
+    x += rng.uniform(-0.01, 0.01, (N, 1)).astype(np.float32)
+    for n in range(N):                                   # a loud burst at a different place in every row
+        a = int(rng.integers(0, T)); x[n, a:a + W // 2] *= 5
+    x[N - 1] = 0.25                                      # a constant row: zero after de-meaning
+    xd = torch.from_numpy(x).cuda()
+    keep = xd.clone()
+    mean, power, maxavg, arg = native.patch_powers(keep, window=W, demean=False)
+    assert torch.equal(keep, xd)
+    mean2, power2, maxavg2, arg2 = native.patch_powers(xd, window=W, demean=True)
+    for a, b in ((mean, mean2), (power, power2), (maxavg, maxavg2), (arg, arg2)):
+        assert torch.equal(a, b)
+    got = xd.cpu().numpy()
+    for n in range(N):
+        want = x[n] - np.mean(x[n])
+        assert np.abs(got[n] - want).max() <= 1e-7
+        assert abs(mean[n].item() - np.mean(x[n])) <= 1e-7
+        assert abs(power[n].item() - np.sum(want ** 2)) <= 1e-5 * max(np.sum(want ** 2), 1e-12)
+        p2, _ = max_avg_power(want, W)
+        assert abs(maxavg[n].item() - p2) <= 1e-5 * max(p2, 1e-6)
+        e = np.sqrt(np.abs(np.convolve(np.pad(want.astype(np.float64) ** 2, (0, W)), np.ones(W) / W, "valid")[:T]))
+        assert e[arg[n].item()] >= e.max() * (1 - 1e-6)
+
+
+class HostPowersOnly:
+    """Hides shift_and_sep_powers so that the callers run the reference's per-row numpy loops."""
+
+    def __init__(self, spot):
+        self.shift_and_sep = spot.shift_and_sep
+
+
+def test_device_powers_give_the_host_loop_results(cuda_device, desk):
+    import copy
+    g, scene, mix, ma = desk
+    from acousticswarms_speech_b200.spot import DataParallelSpotModel
+    spot = DataParallelSpotModel(MeanOverMics(), batch_size=128)
+    patches, _ = ma.Apply_SRP_PHAT(torch.from_numpy(mix))
+    kept_dev = ma.Spotform_Big_Patch(torch.from_numpy(mix), copy.deepcopy(patches), spot)
+    thr_dev = ma.Relative_Threshold
+    kept_host = ma.Spotform_Big_Patch(torch.from_numpy(mix), copy.deepcopy(patches), HostPowersOnly(spot))
+    assert [list(p.sample_offset) for p in kept_dev] == [list(p.sample_offset) for p in kept_host]
+    assert abs(thr_dev - ma.Relative_Threshold) <= 1e-6 * thr_dev
+    out_dev = ma.Spotform_Small_Patch_Parallel(torch.from_numpy(mix), copy.deepcopy(kept_dev[:3]), spot)
+    out_host = ma.Spotform_Small_Patch_Parallel(torch.from_numpy(mix), copy.deepcopy(kept_host[:3]), HostPowersOnly(spot))
+    assert len(out_dev) == len(out_host) > 0
+    for a, b in zip(out_dev, out_host):
+        assert a[3] == b[3] and np.array_equal(a[4]["audio_offset"], b[4]["audio_offset"])
+        assert np.allclose(a[4]["localization_offset"], b[4]["localization_offset"], rtol=1e-5, atol=1e-6)
+        assert np.abs(a[1] - b[1]).max() <= 1e-7 and abs(a[2] - b[2]) <= 1e-5 * b[2]
+
+
 def test_two_mic_array_end_to_end(cuda_device):
     """M = 2: one pair, one TDoA dimension -- exercises D = 1 in scoring, peak picking and patch selection."""
     from acousticswarms_speech_b200.mic_array import Mic_Array
