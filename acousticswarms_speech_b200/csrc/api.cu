@@ -30,6 +30,7 @@ struct asw_srp {
     int device = 0, M = 0, P = 0, G = 0, Gpad = 0;
     int nfft = 0, hop = 0, bin0 = 0, bin1 = 0, F = 0, U = 0;
     float tol = 0.f;
+    int frame_mode = ASW_FRAMES_FLOOR;
     // per-pair lag-table layout (host copies) and device mirrors
     std::vector<int> lag_lo, n_entries, npad, off;
     int tab_len = 0;
@@ -124,6 +125,22 @@ int asw_srp_num_windows(int T, int win_len) {
 int asw_srp_num_frames(int win_len, int nfft, int hop) {
     if (win_len < nfft || hop <= 0) return 0;
     return (win_len - nfft) / hop + 1;
+}
+
+int asw_srp_num_frames_mode(int win_len, int nfft, int hop, int frame_mode) {
+    if (frame_mode == ASW_FRAMES_FLOOR) return asw_srp_num_frames(win_len, nfft, hop);
+    if (win_len < 1 || hop <= 0) return 0;
+    if (win_len < nfft) return 1;                                  // one frame, zero padded
+    return (win_len - nfft + hop - 1) / hop + 1;
+}
+
+int asw_srp_set_frame_mode(asw_srp_t* h, int frame_mode) {
+    if (!h || (frame_mode != ASW_FRAMES_FLOOR && frame_mode != ASW_FRAMES_PAD_TAIL)) {
+        set_error("asw_srp_set_frame_mode: null handle or unknown mode %d", frame_mode);
+        return ASW_ERR_ARG;
+    }
+    h->frame_mode = frame_mode;
+    return ASW_OK;
 }
 
 int asw_srp_create(asw_srp_t** out, int device, int M, int G, const double* lag, int nfft, int hop, int bin0, int bin1,
@@ -306,7 +323,7 @@ int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len,
     }
     cudaStream_t s = (cudaStream_t)stream;
     const int Nw = asw_srp_num_windows(T, win_len);
-    const int Nf = asw_srp_num_frames(win_len, h->nfft, h->hop);
+    const int Nf = asw_srp_num_frames_mode(win_len, h->nfft, h->hop, h->frame_mode);
     if (Nw < 1 || Nf < 1) {
         // no analysis window fits: the reference leaves the map at its zero initialisation (:253)
         ASW_CUDA_CHECK(cudaMemsetAsync(map_dev, 0, sizeof(float) * (size_t)B * h->G, s));
@@ -323,6 +340,7 @@ int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len,
     sp.T = T;
     sp.Nw = Nw;
     sp.step = win_len / 2;
+    sp.win_len = win_len;
     sp.Nf = Nf;
     sp.bin0 = h->bin0;
     sp.F = h->F;

@@ -53,6 +53,7 @@ struct StftCcParams {
     const float2* tw1024;  // [1024]  exp(-2 pi i t / 1024)
     const float2* twpost;  // [F]     exp(-2 pi i k / 2048), k = bin0 + f
     int B, M, T, Nw, step, Nf, NG, FG, bin0, F, P;
+    int win_len;           // samples of one analysis window; frame n holds min(nfft, win_len - n*hop) of them, zeros after
     float tol;
 };
 int launch_stft_cc(const StftCcParams& p, cudaStream_t s);          // generic (any M <= 32)

@@ -75,7 +75,14 @@ __global__ void __launch_bounds__(kThreads) stft_cc_kernel(StftCcParams p) {
             const float* x = p.mix + ((size_t)b * p.M + m) * (size_t)p.T + (size_t)w * p.step + (size_t)n * kHop;
             // pass 0 straight from global: z[t] = x[2t] + i x[2t+1]
             float2 v0, v1, v2, v3;
-            if ((reinterpret_cast<uintptr_t>(x) & 7) == 0) {
+            const int valid = p.win_len - n * kHop;   // < nfft only for the ragged last frame of the tail-padded mode
+            if (valid < kNfft) {
+                auto ld = [&](int i) { return i < valid ? __ldg(x + i) : 0.f; };
+                v0 = make_float2(ld(2 * j), ld(2 * j + 1));
+                v1 = make_float2(ld(2 * (j + 256)), ld(2 * (j + 256) + 1));
+                v2 = make_float2(ld(2 * (j + 512)), ld(2 * (j + 512) + 1));
+                v3 = make_float2(ld(2 * (j + 768)), ld(2 * (j + 768) + 1));
+            } else if ((reinterpret_cast<uintptr_t>(x) & 7) == 0) {
                 const float2* z = reinterpret_cast<const float2*>(x);
                 v0 = __ldg(z + j);
                 v1 = __ldg(z + j + 256);

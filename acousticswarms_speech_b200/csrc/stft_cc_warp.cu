@@ -52,6 +52,22 @@ __device__ __forceinline__ void prefetch_frame(float* tile, const float* x, int 
     cp_async_commit();
 }
 
+// The ragged last frame of the tail-padded frame mode: only `valid` (< 2048) samples belong to the analysis
+// window, the rest of the frame is zeros (the samples that follow in memory belong to the next window).
+__device__ __forceinline__ void prefetch_partial_frame(float* tile, const float* x, int lane, int valid) {
+    for (int i = lane; i < kNfft; i += 32) {
+        if (i < valid) cp_async4(tile + i, x + i);
+        else tile[i] = 0.f;
+    }
+    cp_async_commit();
+}
+
+__device__ __forceinline__ void prefetch_frame_n(float* tile, const float* xw, int n, int win_len, int lane) {
+    const int valid = win_len - n * kHop;
+    if (valid >= kNfft) prefetch_frame(tile, xw + (size_t)n * kHop, lane);
+    else prefetch_partial_frame(tile, xw + (size_t)n * kHop, lane, valid);
+}
+
 template <int M>
 struct Cfg {
     static constexpr int kThreads = 32 * M;
@@ -93,7 +109,7 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
     // The tile is idle between the transposed read of frame n and the transposed write of frame n+1:
     // it doubles as the landing buffer of the cp.async prefetch of frame n+1 (raw layout, 8 KB), so
     // the global-load latency overlaps the second DFT pass, the split/PHAT and the pair products.
-    if (n0 < n1) prefetch_frame(tile, xm + (size_t)n0 * kHop, lane);
+    if (n0 < n1) prefetch_frame_n(tile, xm, n0, p.win_len, lane);
 
     for (int n = n0; n < n1; ++n) {
         float2* px = s_px + (size_t)(n & 1) * M * F;
@@ -112,7 +128,7 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
             __syncwarp();
             load_transposed(v, tile, lane);
             __syncwarp();  // the tile is free again: start fetching the next frame into it
-            if (n + 1 < n1) prefetch_frame(tile, xm + (size_t)(n + 1) * kHop, lane);
+            if (n + 1 < n1) prefetch_frame_n(tile, xm, n + 1, p.win_len, lane);
             dft32(v);      // Z[k1 + 32 k2] at v[bitrev5(k2)], k1 = lane
             // real-input split for bins k = lane + 32 k2, k2 < kK2, then PHAT
             const int partner = (32 - lane) & 31;

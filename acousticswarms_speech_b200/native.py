@@ -47,7 +47,8 @@ def pair_lags(grids, mic_pos, fs, C):
 class NativeSRP:
     """Device-resident scoring handle (asw_srp_t) for one geometry."""
 
-    def __init__(self, lag_samples, num_mic, device=None, bin0=2, bin1=200, tol=PHAT_TOL, oversample=0):
+    def __init__(self, lag_samples, num_mic, device=None, bin0=2, bin1=200, tol=PHAT_TOL, oversample=0,
+                 pad_tail=False):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.AswError("no CUDA device: the SRP-PHAT path is CUDA-only (sm_100a), there is no CPU fallback")
@@ -64,6 +65,18 @@ class NativeSRP:
                                            lag.ctypes.data_as(ctypes.c_void_p), n_fft, HOP, bin0, bin1,
                                            ctypes.c_float(tol), oversample))
         self._last = (0, 0)
+        self.pad_tail = False
+        if pad_tail:
+            self.set_pad_tail(True)
+
+    def set_pad_tail(self, enabled):
+        """STFT framing of an analysis window: False = floor((win - nfft) / hop) + 1 frames (assumption A1),
+        True = ceil(...) + 1 frames with the ragged last frame zero padded (see include/asw.h)."""
+        _lib.check(self.lib.asw_srp_set_frame_mode(self._h, 1 if enabled else 0))
+        self.pad_tail = bool(enabled)
+
+    def num_frames(self, win_len):
+        return int(self.lib.asw_srp_num_frames_mode(int(win_len), n_fft, HOP, 1 if self.pad_tail else 0))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -164,6 +164,14 @@ class SRP_PHAT(object):
         self.Min_POWER = 0.0
 
     # ---- geometry ----------------------------------------------------------------------------
+    def set_stft_pad_tail(self, enabled):
+        """Frame convention of the STFT inside ``SRP_Map_WINDOW_new`` (:406, pyroomacoustics' ``analysis``, not
+        vendored with the reference): False (default, assumption A1) drops the samples that do not fill a frame,
+        True keeps them in one more zero-padded frame.  See ``asw_srp_set_frame_mode`` in include/asw.h."""
+        if self.native is None:
+            raise native._lib.AswError("no device handle (build_native=False)")
+        self.native.set_pad_tail(enabled)
+
     def check_valid(self, idx):
         if idx[0] < 0 or idx[0] >= self.Lx or idx[1] < 0 or idx[1] >= self.Ly or idx[2] < 0 or idx[2] >= self.Lz:
             return False

@@ -92,7 +92,11 @@ def speaker_positions(scene, n_spk, rng):
     bx0, by0 = mic[:, 0].min() - 0.25, mic[:, 1].min() - 0.25
     bx1, by1 = mic[:, 0].max() + 0.25, mic[:, 1].max() + 0.25
     out = []
+    tries = 0
     while len(out) < n_spk:
+        tries += 1
+        if tries > 20000:       # a region too small for n_spk sources MIN_SPEAKER_DIST apart: start over
+            out, tries = [], 0
         p = np.array([rng.uniform(r[0] + 0.1, r[1] - 0.1), rng.uniform(r[2] + 0.1, r[3] - 0.1),
                       rng.uniform(max(r[4], SPK_Z[0]), min(r[5], SPK_Z[1]))])
         if bx0 < p[0] < bx1 and by0 < p[1] < by1:

@@ -70,6 +70,19 @@ int asw_srp_create(asw_srp_t** out, int device, int M, int G, const double* lag_
                    int nfft, int hop, int bin0, int bin1, float tol, int oversample);
 int asw_srp_destroy(asw_srp_t* h);
 
+/* How an analysis window is cut into STFT frames.  The reference calls
+ * pyroomacoustics.transform.stft.analysis(x, nfft, nfft // 4) (SRP_Prunning.py:406; pyroomacoustics==0.5.0,
+ * requirements.txt:10), which is not vendored with it (assumption A1 of DESIGN.md):
+ *   ASW_FRAMES_FLOOR     (default) floor((win - nfft) / hop) + 1 frames, samples that do not fill a frame are dropped;
+ *   ASW_FRAMES_PAD_TAIL  ceil((win - nfft) / hop) + 1 frames, the last one completed with zeros -- the
+ *                        "append zeros" handling of a ragged tail by a non-streaming STFT.
+ * Both are implemented, tested against the oracle, and differ only when (win - nfft) % hop != 0 (36000- and
+ * 24000-sample windows: 67 vs 68 and 43 vs 44 frames).  A maintainer who can run the pinned package re-pins A1
+ * with this one call. */
+enum { ASW_FRAMES_FLOOR = 0, ASW_FRAMES_PAD_TAIL = 1 };
+int asw_srp_set_frame_mode(asw_srp_t* h, int frame_mode);
+int asw_srp_num_frames_mode(int win_len, int nfft, int hop, int frame_mode);
+
 /* SRP_PHAT.SRP_Map_WINDOW_new / SRP_Map_WINDOW_torch
  * (sep/Traditional_SP/SRP_Prunning.py:384-433) for a batch of B mixtures that
  * share the geometry: analysis-window framing (:393-403), rectangular-window

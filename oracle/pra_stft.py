@@ -24,18 +24,27 @@ in this one function so it can be re-pinned in one place.
 import numpy as np
 
 
-def analysis(x, L, hop, win=None, zp_back=0, zp_front=0):
+def analysis(x, L, hop, win=None, zp_back=0, zp_front=0, pad_tail=False):
+    """``pad_tail=False`` is assumption A1 as stated above.  ``pad_tail=True`` is the alternative reading of the
+    same boundary -- a non-streaming STFT that keeps a ragged tail: ``ceil((len - L) / hop) + 1`` frames, the input
+    extended with zeros to fill the last one (one zero-padded frame when ``len < L``).  libasw.so implements both
+    (``asw_srp_set_frame_mode``); they coincide when ``(len - L) % hop == 0``."""
     if win is not None or zp_back or zp_front:
         raise NotImplementedError("only the call shape used by the reference is restated")
     x = np.asarray(x)
     if x.ndim != 1:
         raise NotImplementedError("mono input only (the reference loops over channels)")
-    n = (x.shape[0] - L) // hop + 1
+    ctype = np.complex64 if x.dtype == np.float32 else np.complex128
+    if pad_tail and x.shape[0] > 0:
+        n = 1 if x.shape[0] < L else -(-(x.shape[0] - L) // hop) + 1
+        extra = (n - 1) * hop + L - x.shape[0]
+        if extra > 0:
+            x = np.concatenate([x, np.zeros(extra, dtype=x.dtype)])
+    else:
+        n = (x.shape[0] - L) // hop + 1
     if n <= 0:
-        return np.zeros((0, L // 2 + 1), dtype=np.complex64 if x.dtype == np.float32 else np.complex128)
+        return np.zeros((0, L // 2 + 1), dtype=ctype)
     idx = np.arange(L)[None, :] + hop * np.arange(n)[:, None]
     frames = x[idx].astype(np.float64)
     X = np.fft.rfft(frames, n=L, axis=1)
-    if x.dtype == np.float32:
-        X = X.astype(np.complex64)
-    return X
+    return X.astype(ctype)

@@ -66,9 +66,9 @@ def steering_table_chunk(grids, mic_pos, freq_bins, fs, nfft, C=343.0):
     return mid[:, :, i] * np.conj(mid[:, :, j])
 
 
-def stft_window(seg, nfft, hop):
+def stft_window(seg, nfft, hop, pad_tail=False):
     """:404-409  (M, nfft//2+1, n_frames) complex64."""
-    return np.array([pra_stft.analysis(x, nfft, hop).T for x in seg])
+    return np.array([pra_stft.analysis(x, nfft, hop, pad_tail=pad_tail).T for x in seg])
 
 
 def phat(X, tol=1e-8):
@@ -106,7 +106,7 @@ def contract(CC_flat, grids, mic_pos, freq_bins, fs, nfft, C=343.0, chunk=2048):
 
 
 def score(signal, grids, mic_pos, freq_bins, fs, nfft, window=None, tol=1e-8,
-          C=343.0, stages=False):
+          C=343.0, stages=False, pad_tail=False):
     """SRP_Map_WINDOW_torch (:387-433).  Returns the float64 map (G,) and, with
     ``stages=True``, the per-window intermediates."""
     signal = np.asarray(signal)
@@ -117,7 +117,7 @@ def score(signal, grids, mic_pos, freq_bins, fs, nfft, window=None, tol=1e-8,
     st = {"starts": [], "CC": [], "map_w": []}
     for s0 in window_starts(T, window):
         seg = signal[:, s0:s0 + window]
-        X = stft_window(seg, nfft, nfft // 4)
+        X = stft_window(seg, nfft, nfft // 4, pad_tail)
         pX = phat(X, tol)
         CC = cross_spectra(pX, freq_bins)
         mw = contract(CC, grids, mic_pos, freq_bins, fs, nfft, C)

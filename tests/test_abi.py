@@ -37,6 +37,14 @@ def test_window_and_frame_helpers_match_reference_rules():
     assert lib.asw_srp_num_frames(36000, 2048, 512) == 67
     assert lib.asw_srp_num_frames(24000, 2048, 512) == 43
     assert lib.asw_srp_num_frames(1000, 2048, 512) == 0
+    # the two readings of assumption A1 (include/asw.h, oracle/pra_stft.py)
+    from oracle import pra_stft
+    for win in (36000, 24000, 2048, 2049, 2048 + 512, 12288, 1000):
+        x = np.zeros(win, dtype=np.float32)
+        assert lib.asw_srp_num_frames_mode(win, 2048, 512, 0) == pra_stft.analysis(x, 2048, 512).shape[0]
+        assert lib.asw_srp_num_frames_mode(win, 2048, 512, 1) == pra_stft.analysis(x, 2048, 512, pad_tail=True).shape[0]
+    assert lib.asw_srp_num_frames_mode(36000, 2048, 512, 1) == 68
+    assert lib.asw_srp_num_frames_mode(24000, 2048, 512, 1) == 44
 
 
 def test_argument_validation_reports_errors():

@@ -121,6 +121,43 @@ def test_generic_mic_count(cuda_device):
     assert np.abs(got - want).max() <= TOL * want.max()
 
 
+@pytest.mark.parametrize("n_mics,T", [(4, 48000), (4, 96000), (4, 50003), (10, 48000)])
+def test_tail_padded_frame_mode(cuda_device, small, n_mics, T):
+    """ASW_FRAMES_PAD_TAIL (the other reading of assumption A1): ceil((win - nfft) / hop) + 1 frames, the ragged
+    last frame zero padded -- warp kernel (M = 4, also with rows that are not 16-byte aligned) and generic
+    kernel (M = 10) against the oracle with the same convention; and it is a different map from the default."""
+    if n_mics == 4:
+        scene, geo = small
+    else:
+        scene = synth.table_array(10, np.random.default_rng(4))
+        scene.roi = [2.0, 2.6, 3.2, 3.8, 0.0, 0.4]
+        geo = geometry_oracle.GeometryOracle(scene.mic_positions, scene.roi, build_fine=False)
+    mix = synth.mixture(scene, 2, T, seed=3)
+    win = srp_oracle.window_length(T)
+    srp = _native(scene, geo.grids, pad_tail=True)
+    assert srp.num_frames(win) == -(-(win - n_fft) // (n_fft // 4)) + 1 == srp_oracle.stft_window(
+        mix[:1, :win], n_fft, n_fft // 4, pad_tail=True).shape[2]
+    x = torch.from_numpy(mix).cuda()
+    got = srp.score(x, win).cpu().numpy()[0]
+    want, st = srp_oracle.score(mix, geo.grids, scene.mic_positions, freq_bins, scene.fs, n_fft, stages=True,
+                                pad_tail=True)
+    cc = srp.read_cc().cpu().numpy()[0]
+    ref_cc = np.stack(st["CC"])
+    assert np.abs(cc - ref_cc).max() <= TOL * np.abs(ref_cc).max()
+    assert np.abs(got - want).max() <= TOL * want.max()
+    srp.set_pad_tail(False)
+    base = srp.score(x, win).cpu().numpy()[0]
+    want0 = srp_oracle.score(mix, geo.grids, scene.mic_positions, freq_bins, scene.fs, n_fft)
+    assert np.abs(base - want0).max() <= TOL * want0.max()
+    assert np.abs(base - got).max() > 10 * TOL * want.max()
+    # a window that the frames tile exactly: both conventions are the same computation
+    w2 = n_fft + 20 * (n_fft // 4)
+    a = srp.score(x, w2)
+    srp.set_pad_tail(True)
+    assert srp.num_frames(w2) == 21
+    assert torch.equal(a, srp.score(x, w2))
+
+
 def test_topk(cuda_device):
     from acousticswarms_speech_b200 import native
     rng = np.random.default_rng(0)
