@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kThreads) gcc_kernel(GccParams p) {
 constexpr int kFftWarps = 4;
 constexpr int kTileFloats = 2 * 32 * 33;
 
-__global__ void __launch_bounds__(32 * kFftWarps) gcc_fft_kernel(GccParams p) {
+__global__ void __launch_bounds__(32 * kFftWarps, 5) gcc_fft_kernel(GccParams p) {   // 5 CTAs/SM: <= 96 registers
     extern __shared__ __align__(16) float s_dyn[];
     __shared__ float s_fir[7 * kTaps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(32 * kFftWarps) gcc_fft_kernel(GccParams p) {
     }
     __syncwarp();
 
-    // v[q] = conj(Z[32 q + lane])
-    float2 v[32];
+    // v[q] = conj(Z[32 q + lane]), packed (re, im) for the FFMA2 / FADD2 butterflies of fft32.cuh
+    c64 v[32];
 #pragma unroll
     for (int q = 0; q < 32; ++q) {
         const int k = 32 * q + lane;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(32 * kFftWarps) gcc_fft_kernel(GccParams p) {
             const float2 m = make_float2(1.f - t.y, t.x);                // 1 + i twpost
             z = cadd(z, cmul(xc, m));
         }
-        v[q] = make_float2(0.5f * z.x, -0.5f * z.y);
+        v[q] = pk(0.5f * z.x, -0.5f * z.y);
     }
     const float2 w1 = __ldg(p.tw1024 + lane);
     const float2 w8 = __ldg(p.tw1024 + ((8 * lane) & 1023));
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(32 * kFftWarps) gcc_fft_kernel(GccParams p) {
     const int base = lo - kMargin;
 #pragma unroll
     for (int k2 = 0; k2 < 32; ++k2) {
-        const float2 o = v[bitrev5(k2)];
+        const float2 o = upk(v[bitrev5(k2)]);
         const int l0 = 2 * (lane + 32 * k2);                             // lag of Re z[n]; Im z[n] is lag l0 + 1
         int j = (l0 - base) & (kNfft - 1);                               // R_p has period 2048
         if (j < n_int) s_r1[j] = o.x * p.scale;

@@ -96,11 +96,11 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
     const float2 w16 = __ldg(p.tw1024 + ((16 * lane) & 1023));
     const float2 w24 = __ldg(p.tw1024 + ((24 * lane) & 1023));
 
-    float2 acc[C::kNb][C::kP];
+    c64 acc[C::kNb][C::kP];   // packed (re, im): the pair products run on FFMA2 / FADD2
 #pragma unroll
     for (int i = 0; i < C::kNb; ++i)
 #pragma unroll
-        for (int q = 0; q < C::kP; ++q) acc[i][q] = make_float2(0.f, 0.f);
+        for (int q = 0; q < C::kP; ++q) acc[i][q] = pk(0.f, 0.f);
 
     const int n0 = grp * p.FG;
     const int n1 = min(p.Nf, n0 + p.FG);
@@ -114,11 +114,11 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
     for (int n = n0; n < n1; ++n) {
         float2* px = s_px + (size_t)(n & 1) * M * F;
         {
-            float2 v[32];
+            c64 v[32];
             cp_async_wait_all();
             __syncwarp();
             {
-                const float2* raw = reinterpret_cast<const float2*>(tile);
+                const c64* raw = reinterpret_cast<const c64*>(tile);
 #pragma unroll
                 for (int q = 0; q < 32; ++q) v[q] = raw[32 * q + lane];   // z[t] = x[2t] + i x[2t+1]
             }
@@ -135,12 +135,12 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
 #pragma unroll
             for (int k2 = 0; k2 < kK2; ++k2) {
                 const int k = lane + 32 * k2;
-                const float2 zk = v[bitrev5(k2)];
+                const float2 zk = upk(v[bitrev5(k2)]);
                 // partner value Z[1024 - k]: lane' = (32 - lane) & 31, k2' = 31 - k2 (lane != 0) or 32 - k2 (lane == 0)
-                const float2 give = v[bitrev5(31 - k2)];
+                const float2 give = upk(v[bitrev5(31 - k2)]);
                 float2 zc = make_float2(__shfl_sync(0xffffffffu, give.x, partner),
                                         __shfl_sync(0xffffffffu, give.y, partner));
-                if (lane == 0) zc = v[bitrev5((32 - k2) & 31)];
+                if (lane == 0) zc = upk(v[bitrev5((32 - k2) & 31)]);
                 const int f = k - p.bin0;
                 if (f >= 0 && f < F) {
                     const float2 post = __ldg(p.twpost + f);
@@ -164,13 +164,16 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
                 for (int mm = 0; mm < M; ++mm) a[mm] = px[mm * F + f];
                 int q = 0;
 #pragma unroll
-                for (int ii = 0; ii < M; ++ii)
+                for (int ii = 0; ii < M; ++ii) {
+                    const c64 ai = pk(a[ii].x, a[ii].y), ai_rot = pk(a[ii].y, -a[ii].x);
 #pragma unroll
                     for (int jj = ii + 1; jj < M; ++jj) {
-                        acc[i][q].x += fmaf(a[ii].x, a[jj].x, a[ii].y * a[jj].y);
-                        acc[i][q].y += fmaf(a[ii].y, a[jj].x, -a[ii].x * a[jj].y);
+                        // a_i conj(a_j) = (fma(ai.x, aj.x, ai.y aj.y), fma(ai.y, aj.x, -ai.x aj.y))
+                        const c64 u = fma2(ai, pk(a[jj].x, a[jj].x), mul2(ai_rot, pk(a[jj].y, a[jj].y)));
+                        acc[i][q] = add2(acc[i][q], u);
                         ++q;
                     }
+                }
             }
         }
         // no second barrier: frame n+1 writes the other px buffer, and frame n+2 reuses this one only
@@ -182,7 +185,7 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
         const int f = tid + i * C::kThreads;
         if (f < F) {
 #pragma unroll
-            for (int q = 0; q < C::kP; ++q) cc_out[(size_t)q * F + f] = acc[i][q];   // [pair][bin]: coalesced
+            for (int q = 0; q < C::kP; ++q) cc_out[(size_t)q * F + f] = upk(acc[i][q]);   // [pair][bin]: coalesced
         }
     }
 }
