@@ -123,8 +123,13 @@ __device__ __forceinline__ void dft32(c64 (&v)[32]) {
     }
 }
 
-__device__ __forceinline__ void twiddle_and_transpose(const c64 (&v)[32], float* tile, int lane, float2 w1f, float2 w8,
+// Pass-1 epilogue shared by both users: twiddle Y[k1] (held at v[bitrev5(k1)]) by W_1024^{lane * k1} (seeded
+// exactly every 8 steps from the table) and store transposed into the per-warp tile, a c64[32][33] array:
+// 64-bit accesses are served per half-warp, the row stride of 33 * 8 bytes puts the 16 lanes of a half-warp on 16
+// distinct bank pairs in both directions, so the write (lane-contiguous) and the read (lane-strided) are conflict-free.
+__device__ __forceinline__ void twiddle_and_transpose(const c64 (&v)[32], float* tile_f, int lane, float2 w1f, float2 w8,
                                                       float2 w16, float2 w24) {
+    c64* tile = reinterpret_cast<c64*>(tile_f);
     c64 tw = pk(1.f, 0.f);
     const c64 w1 = pk(w1f.x, w1f.y);
 #pragma unroll
@@ -132,39 +137,15 @@ __device__ __forceinline__ void twiddle_and_transpose(const c64 (&v)[32], float*
         if (k1 == 8) tw = pk(w8.x, w8.y);
         if (k1 == 16) tw = pk(w16.x, w16.y);
         if (k1 == 24) tw = pk(w24.x, w24.y);
-        const float2 y = upk((k1 == 0) ? v[0] : cmul2(v[bitrev5(k1)], tw));
-        tile[k1 * 33 + lane] = y.x;
-        tile[32 * 33 + k1 * 33 + lane] = y.y;
+        tile[k1 * 33 + lane] = (k1 == 0) ? v[0] : cmul2(v[bitrev5(k1)], tw);
         if ((k1 & 7) != 7) tw = cmul2(tw, w1);
     }
 }
 
-__device__ __forceinline__ void load_transposed(c64 (&v)[32], const float* tile, int lane) {
+__device__ __forceinline__ void load_transposed(c64 (&v)[32], const float* tile_f, int lane) {
+    const c64* tile = reinterpret_cast<const c64*>(tile_f);
 #pragma unroll
-    for (int t = 0; t < 32; ++t) v[t] = pk(tile[lane * 33 + t], tile[32 * 33 + lane * 33 + t]);
-}
-
-// Pass-1 epilogue shared by both users: twiddle Y[k1] (held at v[bitrev5(k1)]) by W_1024^{lane * k1}
-// (seeded exactly every 8 steps from the table) and store transposed into the per-warp tile
-// (re[32][33], im[32][33]: conflict-free both ways).
-__device__ __forceinline__ void twiddle_and_transpose(const float2 (&v)[32], float* tile, int lane, float2 w1, float2 w8,
-                                                      float2 w16, float2 w24) {
-    float2 tw = make_float2(1.f, 0.f);
-#pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) {
-        if (k1 == 8) tw = w8;
-        if (k1 == 16) tw = w16;
-        if (k1 == 24) tw = w24;
-        const float2 y = (k1 == 0) ? v[0] : cmul(v[bitrev5(k1)], tw);
-        tile[k1 * 33 + lane] = y.x;
-        tile[32 * 33 + k1 * 33 + lane] = y.y;
-        if ((k1 & 7) != 7) tw = cmul(tw, w1);
-    }
-}
-
-__device__ __forceinline__ void load_transposed(float2 (&v)[32], const float* tile, int lane) {
-#pragma unroll
-    for (int t = 0; t < 32; ++t) v[t] = make_float2(tile[lane * 33 + t], tile[32 * 33 + lane * 33 + t]);
+    for (int t = 0; t < 32; ++t) v[t] = tile[lane * 33 + t];
 }
 
 }  // namespace asw

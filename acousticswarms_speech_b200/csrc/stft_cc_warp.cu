@@ -81,7 +81,7 @@ template <int M>
 __global__ void stft_cc_warp_kernel(StftCcParams p) {
     using C = Cfg<M>;
     extern __shared__ __align__(16) float smem[];
-    // per-warp transpose tile: re[32][33], im[32][33]; then pX double buffer [2][M][F]
+    // per-warp transpose tile: packed complex [32][33] (8448 B, also the landing buffer of the next raw frame); then pX double buffer [2][M][F]
     float* tile = smem + (threadIdx.x >> 5) * (2 * 32 * 33);
     float2* s_px = reinterpret_cast<float2*>(smem + M * (2 * 32 * 33));
     const int lane = threadIdx.x & 31;
