@@ -89,6 +89,7 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
     const int tid = threadIdx.x;
     const int grp = blockIdx.x, w = blockIdx.y, b = blockIdx.z;
     const int F = p.F;
+    const float tol2 = p.tol * p.tol;
 
     // per-lane twiddle seeds W_1024^{t j}, j = 1, 8, 16, 24 (t = lane)
     const float2 w1 = __ldg(p.tw1024 + lane);
@@ -147,9 +148,11 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
                     const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
                     const float2 o = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
                     const float2 X = cadd(e, cmul(post, o));
-                    float mag = sqrtf(fmaf(X.x, X.x, X.y * X.y));
-                    mag = fmaxf(mag, p.tol);
-                    const float inv = 1.0f / mag;
+                    // X / max(|X|, tol) as X * rsqrt(max(|X|^2, tol^2)): one MUFU.RSQ (2^-22 relative) instead of the
+                    // IEEE sqrt + divide sequences with their slow-path branches
+                    const float n2 = fmaxf(fmaf(X.x, X.x, X.y * X.y), tol2);
+                    float inv;
+                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(n2));
                     px[m * F + f] = make_float2(X.x * inv, X.y * inv);
                 }
             }
