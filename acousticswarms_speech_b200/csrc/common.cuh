@@ -82,12 +82,14 @@ int launch_patch_powers(float* x, int N, int T, int W, int demean, float* mean_o
 
 struct SrpGatherParams {
     const float* gcc;       // as above
-    const uint32_t* pos;    // [P][Gpad] Q12.20 position inside the pair's table
+    const uint32_t* pos;    // [P][Gpad] Q12.20 position inside the pair's table, in slot order
+    const int* perm;        // [Gpad] slot -> hypercube index (-1 = padding)
     const int* npad;        // [P]
     const int* off;         // [P]
     const int* grp_begin;   // [n_groups + 1] pair ranges staged together
     float* map;             // [B][G]
     int B, G, Gpad, P, Nw, tab_len, n_groups, smem_bytes;
+    int tile;               // hypercubes per CTA (chosen by launch_srp_gather)
 };
 int launch_srp_gather(const SrpGatherParams& p, cudaStream_t s);
 int srp_gather_windows_per_chunk();

@@ -25,7 +25,10 @@ __global__ void __launch_bounds__(kThreads, kMaxThreads / kThreads) srp_gather_k
     extern __shared__ __align__(16) float s_tab[];
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
-    const int g_base = blockIdx.x * (kThreads * GPT);
+    const int g_base = blockIdx.x * p.tile;   // p.tile <= kThreads * GPT hypercubes per CTA
+    bool on[GPT];
+#pragma unroll
+    for (int gi = 0; gi < GPT; ++gi) on[gi] = gi * kThreads + tid < p.tile;
     const float* gcc_b = p.gcc + (size_t)b * p.tab_len * p.Nw;
 
     float best[GPT];
@@ -59,7 +62,9 @@ __global__ void __launch_bounds__(kThreads, kMaxThreads / kThreads) srp_gather_k
                 const int npd = p.npad[pp];
 #pragma unroll
                 for (int gi = 0; gi < GPT; ++gi) {
-                    const uint32_t q = __ldg(p.pos + (size_t)pp * p.Gpad + g_base + gi * kThreads + tid);
+                    if (!on[gi]) continue;
+                    const uint32_t q =
+                        __ldg(p.pos + (size_t)pp * p.Gpad + min(g_base + gi * kThreads + tid, p.Gpad - 1));
                     const int i0 = (int)(q >> kFracBits);
                     const float f = (float)(q & ((1u << kFracBits) - 1)) * (1.0f / (float)(1 << kFracBits));
                     // 4-tap Lagrange weights for nodes -1, 0, 1, 2
@@ -93,24 +98,47 @@ __global__ void __launch_bounds__(kThreads, kMaxThreads / kThreads) srp_gather_k
     }
 #pragma unroll
     for (int gi = 0; gi < GPT; ++gi) {
-        const int g = g_base + gi * kThreads + tid;
-        if (g < p.G) p.map[(size_t)b * p.G + g] = best[gi];
+        const int slot = g_base + gi * kThreads + tid;
+        if (on[gi] && slot < p.G) p.map[(size_t)b * p.G + p.perm[slot]] = best[gi];
     }
 }
 
 template <int GPT, int kThreads>
-int launch_t(const SrpGatherParams& p, cudaStream_t s) {
+int launch_t(SrpGatherParams p, int tile, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
         ASW_CUDA_CHECK(cudaFuncSetAttribute(srp_gather_kernel<GPT, kThreads>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         attr_set = true;
     }
-    const int tile = kThreads * GPT;
+    p.tile = tile;
     dim3 grid((p.G + tile - 1) / tile, p.B);
     srp_gather_kernel<GPT, kThreads><<<grid, kThreads, p.smem_bytes, s>>>(p);
     ASW_LAUNCH_CHECK("srp_gather_kernel");
     return ASW_OK;
+}
+
+// Hypercubes per CTA.  Every CTA stages the mixture's whole GCC table (cost ~ s_eq hypercubes' worth of gathers)
+// and one CTA fits per SM, so the kernel runs in ceil(CTAs / 148) rounds of (s_eq + tile): pick the tile that
+// minimises it -- e.g. G = 21181, B = 32: 2048 -> 352 CTAs = 2.4 rounds, 1632 -> 416 CTAs = 2.8 rounds.
+int choose_tile(int G, int B, int P, int tab_len) {
+    const int kMinTile = 512, kMaxTile = 2 * kMaxThreads;
+    const double s_eq = 0.2 * (double)tab_len / (double)(P > 0 ? P : 1);
+    int best_tile = kMaxTile;
+    double best_cost = 1e300;
+    for (int nt = (G + kMaxTile - 1) / kMaxTile; nt <= (G + kMinTile - 1) / kMinTile; ++nt) {
+        int tile = ((G + nt - 1) / nt + 31) / 32 * 32;
+        if (tile > kMaxTile) continue;
+        if (tile < kMinTile) tile = kMinTile;
+        const long long ctas = (long long)B * ((G + tile - 1) / tile);
+        const long long rounds = (ctas + kNumSms - 1) / kNumSms;
+        const double cost = (double)rounds * (s_eq + tile);
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best_tile = tile;
+        }
+    }
+    return best_tile;
 }
 
 }  // namespace
@@ -123,10 +151,9 @@ int launch_srp_gather(const SrpGatherParams& p, cudaStream_t s) {
         set_error("srp_gather: stage of %d bytes exceeds the shared-memory budget", p.smem_bytes);
         return ASW_ERR_RANGE;
     }
-    // Larger tiles amortise the table staging; smaller tiles fill the 148 SMs when the batch is small.
-    const long long tiles2 = (long long)((p.G + kMaxThreads * 2 - 1) / (kMaxThreads * 2)) * p.B;
-    if (tiles2 >= kNumSms) return launch_t<2, kMaxThreads>(p, s);
-    return launch_t<1, kMaxThreads>(p, s);
+    const int tile = choose_tile(p.G, p.B, p.P, p.tab_len);
+    if (tile > kMaxThreads) return launch_t<2, kMaxThreads>(p, tile, s);
+    return launch_t<1, kMaxThreads>(p, tile, s);
 }
 
 }  // namespace asw
