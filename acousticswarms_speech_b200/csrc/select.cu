@@ -38,6 +38,7 @@ struct asw_select {
     double* d_xx5 = nullptr;      // [Nx5]
     double* d_yy5 = nullptr;      // [Ny5]
     double* d_off1 = nullptr;     // [Ny1][Nx1][Nz][D]
+    double* d_grid1 = nullptr;    // [Nx1 + Ny1 + Nz] coordinates of the 1 cm volume (asw_select_set_grid1), optional
     unsigned char* d_box = nullptr;  // [G] is the untrimmed box of cluster g non-empty
     // subdivision workspace (grown on demand): per candidate one area list and two ping-pong node lists
     int32_t* d_lists = nullptr;
@@ -405,6 +406,8 @@ struct SubParams {
     int32_t* leaf_w;                // [n][max_leaves][D]
     int32_t* leaf_npts;             // [n][max_leaves]
     double* leaf_box;               // [n][max_leaves][2][D]
+    double* leaf_centre;            // [n][max_leaves][3] mean position of the leaf's member voxels (optional)
+    const double* grid1;            // xx1 [Nx1], yy1 [Ny1], zz [Nz]
     int32_t* root_after;            // [n][2][D] root offsets / widths after check_out (the reference mutates the candidate)
     int32_t* status;                // [n] 0 ok, 1 member list overflow, 2 node overflow, 3 leaf overflow
 };
@@ -420,6 +423,7 @@ __global__ void __launch_bounds__(kSubThreads) subdivide_kernel(SubParams q) {
     __shared__ int s_n, s_cnt[kSubD][2], s_pos[2], s_flag[4];
     __shared__ double s_blo[kSubD], s_bhi[kSubD], s_hlo[kSubD][2], s_hhi[kSubD][2];
     __shared__ int s_elig[kSubD], s_hc[kSubD][2], s_hw[kSubD];
+    __shared__ double s_sum[kSubThreads / 32][3];
     const SelectParams& p = q.g;
     const int tid = threadIdx.x, lane = tid & 31;
     const int cand = blockIdx.x, D = p.D;
@@ -601,6 +605,37 @@ __global__ void __launch_bounds__(kSubThreads) subdivide_kernel(SubParams q) {
                 if (chosen < 0) leaf = true;
             }
             if (leaf) {
+                if (q.leaf_centre && n_leaf < q.max_leaves) {
+                    // Patch.center_pos() of the leaf: mean of its member voxels' positions (Patch_3D.py, np.mean of
+                    // area_points); summed per thread, per warp, then over the warps in a fixed order
+                    double sx = 0.0, sy = 0.0, sz = 0.0;
+                    for (int k = tid; k < nd->count; k += kSubThreads) {
+                        const int vox = src[nd->start + k];
+                        const int iz = vox % p.Nz, r2 = vox / p.Nz;
+                        const int ix = r2 % p.Nx1, iy = r2 / p.Nx1;
+                        sx += q.grid1[ix];
+                        sy += q.grid1[p.Nx1 + iy];
+                        sz += q.grid1[p.Nx1 + p.Ny1 + iz];
+                    }
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) {
+                        sx += __shfl_xor_sync(0xffffffffu, sx, d);
+                        sy += __shfl_xor_sync(0xffffffffu, sy, d);
+                        sz += __shfl_xor_sync(0xffffffffu, sz, d);
+                    }
+                    if (lane == 0) {
+                        s_sum[tid >> 5][0] = sx;
+                        s_sum[tid >> 5][1] = sy;
+                        s_sum[tid >> 5][2] = sz;
+                    }
+                    __syncthreads();
+                    if (tid < 3) {
+                        double t = 0.0;
+                        for (int w = 0; w < kSubThreads / 32; ++w) t += s_sum[w][tid];
+                        q.leaf_centre[((size_t)cand * q.max_leaves + n_leaf) * 3 + tid] =
+                            nd->count > 0 ? t / (double)nd->count : nan("");
+                    }
+                }
                 if (tid == 0) {
                     if (n_leaf < q.max_leaves) {
                         const size_t lb = (size_t)cand * q.max_leaves + n_leaf;
@@ -848,6 +883,7 @@ int asw_select_destroy(asw_select_t* h) {
     cudaFree(h->d_vox5);
     cudaFree(h->d_bstart);
     cudaFree(h->d_xx5);
+    cudaFree(h->d_grid1);
     cudaFree(h->d_yy5);
     cudaFree(h->d_off1);
     cudaFree(h->d_box);
@@ -893,10 +929,28 @@ int asw_select_patches(asw_select_t* h, const float* map_dev, const int32_t* pea
     return ASW_OK;
 }
 
+int asw_select_set_grid1(asw_select_t* h, const double* xx1, const double* yy1, const double* zz) {
+    if (!h || !xx1 || !yy1 || !zz) {
+        set_error("asw_select_set_grid1: null argument");
+        return ASW_ERR_ARG;
+    }
+    ASW_CUDA_CHECK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->Nx1 + h->Ny1 + h->Nz;
+    if (!h->d_grid1) ASW_CUDA_CHECK(cudaMalloc(&h->d_grid1, n * sizeof(double)));
+    ASW_CUDA_CHECK(cudaMemcpy(h->d_grid1, xx1, sizeof(double) * h->Nx1, cudaMemcpyHostToDevice));
+    ASW_CUDA_CHECK(cudaMemcpy(h->d_grid1 + h->Nx1, yy1, sizeof(double) * h->Ny1, cudaMemcpyHostToDevice));
+    ASW_CUDA_CHECK(cudaMemcpy(h->d_grid1 + h->Nx1 + h->Ny1, zz, sizeof(double) * h->Nz, cudaMemcpyHostToDevice));
+    return ASW_OK;
+}
+
 int asw_subdivide(asw_select_t* h, const int32_t* centres_dev, const int32_t* widths_dev, int n,
                   const double* upper_bound, int max_leaves, int32_t* leaf_count_dev, int32_t* leaf_off_dev,
-                  int32_t* leaf_w_dev, int32_t* leaf_npts_dev, double* leaf_box_dev, int32_t* root_after_dev,
-                  int32_t* status_dev, void* stream) {
+                  int32_t* leaf_w_dev, int32_t* leaf_npts_dev, double* leaf_box_dev, double* leaf_centre_dev,
+                  int32_t* root_after_dev, int32_t* status_dev, void* stream) {
+    if (leaf_centre_dev && (!h || !h->d_grid1)) {
+        set_error("asw_subdivide: leaf centres need the 1 cm grid coordinates (asw_select_set_grid1)");
+        return ASW_ERR_ARG;
+    }
     if (!h || !centres_dev || !widths_dev || !upper_bound || !leaf_count_dev || !leaf_off_dev || !leaf_w_dev ||
         !leaf_npts_dev || !leaf_box_dev || !root_after_dev || !status_dev || n < 0 || max_leaves < 1) {
         set_error("asw_subdivide: null argument or bad shape");
@@ -932,6 +986,8 @@ int asw_subdivide(asw_select_t* h, const int32_t* centres_dev, const int32_t* wi
     q.leaf_w = leaf_w_dev;
     q.leaf_npts = leaf_npts_dev;
     q.leaf_box = leaf_box_dev;
+    q.leaf_centre = leaf_centre_dev;
+    q.grid1 = h->d_grid1;
     q.root_after = root_after_dev;
     q.status = status_dev;
     const size_t smem = 2 * (size_t)kMaxNodes * sizeof(SubNode);

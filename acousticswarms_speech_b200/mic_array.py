@@ -12,6 +12,7 @@ import torch
 from .constants import (FS, INIT_WIDTH, SPEED_OF_SOUND, SPOT_POWER_THRESHOLD2, SRP_THRESHOLDS,
                         USE_RELATIVE_SPOT_POWER, freq_bins, n_fft, window_length)
 from .local_utils import _tdoa_rows, binary_search_baseline, max_avg_power, search_area, si_sdr
+from .spot import si_sdr_from_gram
 from .patch import Patch
 from .srp_phat import SRP_PHAT
 
@@ -109,13 +110,13 @@ class Mic_Array(object):
         for c in candidates:
             if not np.all(np.asarray(c.width_list) == c.width_list[0]):
                 raise native._lib.AswError("coarse patches must have one width in every dimension")
-        cn, off, wid, npts, box, root = native.subdivide(node.native_select, torch.from_numpy(centres).to(dev),
+        cn, off, wid, npts, box, root, centre = native.subdivide(node.native_select, torch.from_numpy(centres).to(dev),
                                                          torch.from_numpy(widths).to(dev), self.upper_bound_pairwise)
         out = []
         for i, cand in enumerate(candidates):
             root_box_lo = centres[i].astype(np.float64) - (float(widths[i]) + 0.2) / 2
             untouched = cn[i] == 1 and np.array_equal(box[i, 0, 0], root_box_lo)    # the root itself is the leaf
-            parent_area = cand.area_points
+            parent = cand.area_points_getter()         # bound before check_out mutates the candidate; built on demand
             cand.sample_offset[:] = root[i, 0]
             cand.width_list[:] = root[i, 1]
             if untouched:
@@ -124,8 +125,9 @@ class Mic_Array(object):
 
             rows_cache = {}
 
-            def builder(lo, hi, area=parent_area, cache=rows_cache):
+            def builder(lo, hi, parent=parent, cache=rows_cache):
                 def build():
+                    area = parent()
                     if "rows" not in cache:              # the candidate's TDoA rows, once for all its leaves
                         cache["rows"] = _tdoa_rows(area, self.mic_positions)
                     rows = cache["rows"]
@@ -133,8 +135,10 @@ class Mic_Array(object):
                     return area[:, keep]
                 return build
 
+            # an empty leaf has no centre (center_pos() -> None, like the host path); the others carry the device mean
             out.append([Patch(off[i, l].astype(np.int64), wid[i, l].astype(np.int64), None, None,
-                              area_fn=builder(box[i, l, 0].copy(), box[i, l, 1].copy())) for l in range(int(cn[i]))])
+                              area_fn=builder(box[i, l, 0].copy(), box[i, l, 1].copy()),
+                              centre=centre[i, l].copy() if npts[i, l] > 0 else None) for l in range(int(cn[i]))])
         return out
 
     def small_patch_list(self, candidate_finished):
@@ -150,7 +154,7 @@ class Mic_Array(object):
                 patch_processed = fine_lists[ci]
             else:
                 patch_processed = search_area([cand], self.mic_positions, self.upper_bound_pairwise)
-            init_area_total.append(cand.area_points)
+            init_area_total.append(cand.area_points_getter())    # (:246) materialised only for clusters that are output
             patch_center0 = Patch(cand.sample_offset, width_list0, None, cand.peak_pos)
             centre = patch_center0.center_pos()
             centre_total.append(centre)
@@ -170,12 +174,16 @@ class Mic_Array(object):
         else:
             thr_new = SPOT_POWER_THRESHOLD2
         total_patch, patches_indexes, init_area_total, centre_total = self.small_patch_list(candidate_finished)
-        device_powers = getattr(spot_model, "shift_and_sep_powers", None)
-        if device_powers is not None:       # rows come back de-meaned, with both powers, from one launch
-            sep_data_total, power_total, power2_total = device_powers(mix_data, total_patch, Strict=1)
+        device_rows = getattr(spot_model, "shift_and_sep_device", None)
+        if device_rows is not None:
+            # outputs stay on the device: per-row powers come back as small arrays, SI-SDR is evaluated from one
+            # Gram matrix of the rows that pass the power gates, and only the audio that is returned is copied
+            rows = device_rows(mix_data, total_patch, Strict=1)
+            sep_data_total = None
         else:
+            rows = None
             sep_data_total = spot_model.shift_and_sep(mix_data, total_patch, Strict=1)
-            power_total = power2_total = None
+        T = mix_data.shape[-1]
 
         for i in range(len(patches_indexes) - 1):
             big_offset = candidate_finished[i].sample_offset
@@ -185,15 +193,15 @@ class Mic_Array(object):
                     if np.amax(np.abs(big_offset - sample_gt[:, k])) < 3.5:
                         big_label = k
                         break
-            sep_data = sep_data_total[patches_indexes[i]:patches_indexes[i + 1]]
-            patch_processed = total_patch[patches_indexes[i]:patches_indexes[i + 1]]
-            init_area = init_area_total[i]
+            lo, hi = patches_indexes[i], patches_indexes[i + 1]
+            patch_processed = total_patch[lo:hi]
+            init_area = init_area_total[i]               # callable: the candidate's area_points on demand
             Big_patch_center = centre_total[i]
-            powers, powers2 = [], []
-            if power_total is not None:
-                powers = list(power_total[patches_indexes[i]:patches_indexes[i + 1]])
-                powers2 = list(power2_total[patches_indexes[i]:patches_indexes[i + 1]])
+            if rows is not None:
+                powers, powers2 = list(rows.power[lo:hi]), list(rows.maxavg[lo:hi])
             else:
+                sep_data = sep_data_total[lo:hi]
+                powers, powers2 = [], []
                 for j in range(len(patch_processed)):
                     sep_data[j, :] = sep_data[j, :] - np.mean(sep_data[j, :])
                     powers.append(np.sum(sep_data[j, :] ** 2))
@@ -205,15 +213,27 @@ class Mic_Array(object):
             sort_idx = np.argsort(-1 * np.array(powers))
             SI_SDR_THRESHOLD = -4
             clusters = {}
-            MIN_TRIGGER_POWER2 = self.MIN_TRIGGER_POWER / (3 * 48000) * sep_data.shape[1]
+            MIN_TRIGGER_POWER2 = self.MIN_TRIGGER_POWER / (3 * 48000) * T
+            passing = []
             for _id in sort_idx:
-                unique = True
                 d = np.linalg.norm(patch_processed[_id].center_pos() - self.mic_positions[0])
                 if powers2[_id] < thr_new / (1 + d) or powers[_id] < MIN_TRIGGER_POWER2:
                     continue
+                passing.append(int(_id))
+            if rows is not None:
+                gram = rows.gram([lo + _id for _id in passing])
+                slot = {_id: k for k, _id in enumerate(passing)}
+
+                def sdr(est, ref):
+                    return si_sdr_from_gram(gram[slot[est], slot[est]], gram[slot[ref], slot[ref]], gram[slot[est], slot[ref]])
+            else:
+                def sdr(est, ref):
+                    return si_sdr(sep_data[est, :], sep_data[ref])
+            for _id in passing:
+                unique = True
                 for cluster_id in clusters:
                     final_candidate_id = clusters[cluster_id][0]
-                    if si_sdr(sep_data[_id, :], sep_data[final_candidate_id]) > SI_SDR_THRESHOLD:
+                    if sdr(_id, final_candidate_id) > SI_SDR_THRESHOLD:
                         clusters[final_candidate_id].append(_id)
                         unique = False
                         break
@@ -221,9 +241,10 @@ class Mic_Array(object):
                     clusters[_id] = [_id]
             for cluster_id in clusters:
                 position, offests = weight_mean_pos(patch_processed, powers, clusters[cluster_id])
-                patch_center = find_merge_center(offests, init_area, self.mic_positions, Big_patch_center)
+                patch_center = find_merge_center(offests, init_area(), self.mic_positions, Big_patch_center)
                 save_offsets = {"audio_offset": patch_processed[cluster_id].sample_offset,
                                 "localization_offset": offests}
-                output_pair.append((patch_center, sep_data[cluster_id, :], powers[cluster_id],
+                audio = rows.row(lo + cluster_id) if rows is not None else sep_data[cluster_id, :]
+                output_pair.append((patch_center, audio, powers[cluster_id],
                                     str(i) + "_" + str(cluster_id), save_offsets, big_label))
         return output_pair

@@ -226,6 +226,12 @@ class NativeSelect:
                                               vox5.ctypes.data, bucket_start.ctypes.data, b0min, b1min, NB0, NB1,
                                               o5.shape[0], Nx5, Ny5, xx5.ctypes.data,
                                               yy5.ctypes.data, axis.ctypes.data, off1.ctypes.data, Ny1, Nx1, Nz))
+        # coordinates of the 1 cm volume (SRP_Prunning.py:158-160), for the leaf centres of asw_subdivide
+        xx1 = np.ascontiguousarray(np.arange(r[0], r[1], 0.01))
+        yy1 = np.ascontiguousarray(np.arange(r[2], r[3], 0.01))
+        zz = np.ascontiguousarray(np.arange(r[4], r[5], 0.1))
+        assert xx1.shape[0] == Nx1 and yy1.shape[0] == Ny1 and zz.shape[0] == Nz
+        _lib.check(self.lib.asw_select_set_grid1(self._h, xx1.ctypes.data, yy1.ctypes.data, zz.ctypes.data))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -258,7 +264,8 @@ class NativeSelect:
 def subdivide(select_handle, centres, widths, upper_bound, max_leaves=128):
     """Device search_area for n coarse patches.  centres (n, D) int32 CUDA, widths (n,) int32 CUDA,
     upper_bound (D,) float64 host.  Returns host numpy arrays
-    (leaf_count (n,), leaf_off (n, L, D), leaf_w (n, L, D), leaf_npts (n, L), leaf_box (n, L, 2, D), root_after (n, 2, D))."""
+    (leaf_count (n,), leaf_off (n, L, D), leaf_w (n, L, D), leaf_npts (n, L), leaf_box (n, L, 2, D),
+    root_after (n, 2, D), leaf_centre (n, L, 3))."""
     _require_cuda(centres, "centres", torch.int32)
     _require_cuda(widths, "widths", torch.int32)
     n, D = centres.shape
@@ -271,17 +278,19 @@ def subdivide(select_handle, centres, widths, upper_bound, max_leaves=128):
     wid = torch.zeros((n, max_leaves, D), device=dev, dtype=torch.int32)
     npts = torch.zeros((n, max_leaves), device=dev, dtype=torch.int32)
     box = torch.zeros((n, max_leaves, 2, D), device=dev, dtype=torch.float64)
+    centre = torch.zeros((n, max_leaves, 3), device=dev, dtype=torch.float64)
     root = torch.zeros((n, 2, D), device=dev, dtype=torch.int32)
     status = torch.zeros((n,), device=dev, dtype=torch.int32)
     if n:
         _lib.check(select_handle.lib.asw_subdivide(select_handle._h, _ptr(centres), _ptr(widths), n, ub.ctypes.data,
                                                    int(max_leaves), _ptr(cnt), _ptr(off), _ptr(wid), _ptr(npts),
-                                                   _ptr(box), _ptr(root), _ptr(status), _stream(dev)))
+                                                   _ptr(box), _ptr(centre), _ptr(root), _ptr(status), _stream(dev)))
     st = status.cpu().numpy()
     cn = cnt.cpu().numpy()
     if (st != 0).any() or (cn > max_leaves).any():
         raise _lib.AswError(f"asw_subdivide: capacity exceeded (status {st.tolist()}, leaves {cn.tolist()})")
-    return cn, off.cpu().numpy(), wid.cpu().numpy(), npts.cpu().numpy(), box.cpu().numpy(), root.cpu().numpy()
+    return (cn, off.cpu().numpy(), wid.cpu().numpy(), npts.cpu().numpy(), box.cpu().numpy(), root.cpu().numpy(),
+            centre.cpu().numpy())
 
 
 def build_shift_table(n_patches, offsets, capacity, shifts=None, mix_index=None, n_total=None):

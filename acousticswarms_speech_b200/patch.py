@@ -7,11 +7,12 @@ import numpy as np
 
 
 class Patch(object):
-    def __init__(self, sample_offset, width_list, area_points, peak_pos=None, area_fn=None):
+    def __init__(self, sample_offset, width_list, area_points, peak_pos=None, area_fn=None, centre=None):
         self.sample_offset = sample_offset          # int64 (M-1,): hypercube centre, samples vs mic 0
         self.width_list = np.copy(width_list)       # full width per dimension (8 coarse, 4 fine, 2 centre)
         self._area_points = area_points             # (3, n) 1 cm voxels inside, or None
         self._area_fn = area_fn                     # builds area_points on first use (device-selected patches)
+        self._centre = centre                       # mean of area_points when the device already reduced it
         self.num_pair = sample_offset.shape[0]
         self.peak_pos = peak_pos
 
@@ -28,6 +29,12 @@ class Patch(object):
     def area_points(self, value):
         self._area_points = value
         self._area_fn = None
+        self._centre = None
+
+    def area_points_getter(self):
+        """A callable returning ``area_points`` (building them on first call).  Lets callers hold on to a patch's
+        points without forcing the 1 cm scan before they are needed."""
+        return lambda: self.area_points
 
     def area_size(self):
         if self.area_points is None or self.area_points.shape[1] == 0:
@@ -37,6 +44,8 @@ class Patch(object):
     def center_pos(self):
         if self.peak_pos is not None:
             return self.peak_pos
+        if self._area_points is None and self._centre is not None:     # asw_subdivide's leaf centre
+            return self._centre
         if self.area_points is None or self.area_points.shape[1] == 0:
             return None
         return np.mean(self.area_points, axis=1)

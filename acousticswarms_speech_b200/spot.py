@@ -29,6 +29,42 @@ def unnormalize_input(data, means, stds):
     return data * stds + means
 
 
+class SepRows:
+    """Separator outputs of one ``shift_and_sep`` call kept on the device, de-meaned (Mic_Array.py:291):
+    ``power[j] = sum(x_j^2)`` (:292) and ``maxavg[j] = max_avg_power(x_j)[0]`` (:293) are host arrays; ``row(j)``
+    copies one output to the host when a caller really needs the audio; ``gram(ids)`` returns the float64 inner
+    products <x_a, x_b> that SI-SDR (eval_utils.py:11-39) is a function of."""
+
+    def __init__(self, x, power, maxavg):
+        self.x, self.power, self.maxavg = x, power, maxavg
+        self._rows = {}
+
+    @property
+    def shape(self):
+        return tuple(self.x.shape)
+
+    def row(self, j):
+        j = int(j)
+        if j not in self._rows:
+            self._rows[j] = self.x[j].cpu().numpy()
+        return self._rows[j]
+
+    def gram(self, ids):
+        if len(ids) == 0:
+            return np.zeros((0, 0))
+        sel = self.x[torch.as_tensor(list(ids), device=self.x.device, dtype=torch.int64)].double()
+        return (sel @ sel.t()).cpu().numpy()
+
+
+def si_sdr_from_gram(ee, rr, er):
+    """Scale-invariant SDR in dB (eval_utils.py:11-39) from <est,est>, <ref,ref>, <est,ref>:
+    a = <ref,est>/<ref,ref>, e_true = a ref, e_res = est - e_true."""
+    a = er / rr
+    true = a * a * rr
+    res = max(ee - 2.0 * a * er + true, 0.0)
+    return 10 * np.log10(true / (res + 1e-8))
+
+
 class DataParallelSpotModel(nn.Module):
     def __init__(self, model, use_fp16=False, batch_size=SPOT_BATCH_SIZE, device=None, data_parallel=True):
         super().__init__()
@@ -80,6 +116,14 @@ class DataParallelSpotModel(nn.Module):
         if save_input:
             return out, saved
         return out
+
+    def shift_and_sep_device(self, input_channels, patch_list, Strict=0, window=12000):
+        """``shift_and_sep`` whose outputs stay on the device: -> ``SepRows`` (per-row power statistics on the host,
+        audio rows and their Gram matrix fetched on demand)."""
+        results, _ = self._shift_and_sep_device(input_channels, patch_list, Strict, False)
+        x = results.float().contiguous()
+        _, power, maxavg, _ = native.patch_powers(x, window=window, demean=True)
+        return SepRows(x, power.cpu().numpy(), maxavg.cpu().numpy())
 
     def shift_and_sep_powers(self, input_channels, patch_list, Strict=0, window=12000):
         """``shift_and_sep`` followed, still on the device, by what every caller does next with each row

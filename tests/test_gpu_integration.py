@@ -419,6 +419,16 @@ def test_device_subdivision_equals_host(cuda_device, desk):
                 want = [local_utils.search_area([c], scene.mic_positions, ub) for c in host_c]
                 got = ma._search_area_device(dev_c)
                 for w, gl, hc, dc in zip(want, got, host_c, dev_c):
+                    # center_pos() of a leaf: the device mean of its member voxels, available without building
+                    # area_points, equal to np.mean over the host leaf's points (different summation order)
+                    for a, b in zip(gl, w):
+                        if a is dc:                                # the candidate itself came back as the only leaf
+                            continue
+                        ca, cb = a.center_pos(), b.center_pos()
+                        assert a._area_points is None
+                        assert (ca is None) == (cb is None)
+                        if cb is not None:
+                            assert np.abs(ca - cb).max() <= 1e-12
                     assert [list(p.sample_offset) for p in gl] == [list(p.sample_offset) for p in w]
                     assert [list(p.width_list) for p in gl] == [list(p.width_list) for p in w]
                     assert [p.area_size() for p in gl] == [p.area_size() for p in w]
