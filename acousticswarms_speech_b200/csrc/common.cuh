@@ -90,6 +90,7 @@ struct SrpGatherParams {
     float* map;             // [B][G]
     int B, G, Gpad, P, Nw, tab_len, n_groups, smem_bytes;
     int tile;               // hypercubes per CTA (chosen by launch_srp_gather)
+    int stage_floats;       // floats per stage buffer (two stages)
 };
 int launch_srp_gather(const SrpGatherParams& p, cudaStream_t s);
 int srp_gather_windows_per_chunk();

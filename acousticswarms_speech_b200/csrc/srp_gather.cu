@@ -5,12 +5,13 @@
 //   :428-429  map_w[g] = sum_{f,p} Re(CC[f,p] tab[g,f,p]) / F / P    == sum_p R_p(tau[g,p])  (see gcc.cu)
 //   :253,:430 SRP_map = maximum(SRP_map, map_w), SRP_map starts at zeros  (so the map is >= 0)
 //
-// Staging is pair-major: a group of pairs x up to kWc windows of GCC table is copied to shared
-// memory, each thread then takes its hypercubes' fixed-point lag positions for those pairs (one
-// coalesced load, reused by every window and computed once into 4-tap Lagrange weights), and
-// gathers 4 adjacent table entries per (hypercube, pair, window).  The per-window sums stay in
-// registers; the max over windows is taken at the end.  The kernel is shared-memory-bandwidth
-// bound (16 B per gather).
+// Staging is pair-major and double buffered: a group of pairs x up to kWc windows of GCC table is copied to one of
+// two shared-memory stages with cp.async while the threads gather from the other one.  Each thread takes its
+// hypercubes' fixed-point lag positions for the staged pairs (one coalesced load, reused by every window and computed
+// once into 4-tap Lagrange weights), and gathers 4 adjacent table entries per (hypercube, pair, window).  The
+// per-window sums stay in registers; the max over windows is taken at the end.  Hypercubes are visited in the k-d
+// order built by asw_srp_create (a warp's 32 hypercubes are neighbours in every pair's table), results are written
+// back through the slot -> hypercube permutation.  The kernel is shared-memory-bandwidth bound (16 B per gather).
 #include "common.cuh"
 
 namespace asw {
@@ -18,7 +19,8 @@ namespace {
 
 constexpr int kMaxThreads = 1024;        // 32 warps hide the shared-memory gather latency (ncu: short_scoreboard)
 constexpr int kWc = 8;                    // windows per staging chunk
-constexpr int kSmemBudget = 200 * 1024;   // bytes of GCC table staged at once
+constexpr int kSmemBudget = 100 * 1024;   // bytes of GCC table per stage; two stages: one is gathered from while the
+                                          // next is being filled by cp.async
 
 template <int GPT, int kThreads>
 __global__ void __launch_bounds__(kThreads, kMaxThreads / kThreads) srp_gather_kernel(SrpGatherParams p) {
@@ -43,21 +45,32 @@ __global__ void __launch_bounds__(kThreads, kMaxThreads / kThreads) srp_gather_k
 #pragma unroll
             for (int gi = 0; gi < GPT; ++gi) acc[w][gi] = 0.f;
 
+        // asynchronous copy of one group of pair tables (this chunk's windows) into a stage buffer
+        auto stage = [&](int grp, float* buf) {
+            const int q0 = p.grp_begin[grp], q1 = p.grp_begin[grp + 1];
+            int so = 0;
+            for (int pp = q0; pp < q1; ++pp) {
+                const int npd = p.npad[pp];
+                const float* src = gcc_b + (size_t)p.Nw * p.off[pp] + (size_t)w0 * npd;
+                const int n4 = (wc * npd) >> 2;
+                for (int i = tid; i < n4; i += kThreads) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                                     (unsigned)__cvta_generic_to_shared(buf + so + 4 * i)),
+                                 "l"(src + 4 * i));
+                }
+                so += wc * npd;
+            }
+            asm volatile("cp.async.commit_group;\n" ::);
+        };
+        __syncthreads();  // the previous chunk's last stage is no longer read
+        stage(0, s_tab);
         for (int grp = 0; grp < p.n_groups; ++grp) {
             const int p0 = p.grp_begin[grp], p1 = p.grp_begin[grp + 1];
-            __syncthreads();  // everyone is done reading the previous stage
+            const float* s_cur = s_tab + (grp & 1) * p.stage_floats;
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");   // this thread's part of group `grp` has landed
+            __syncthreads();  // everybody's part has, and everybody is done gathering from the other stage
+            if (grp + 1 < p.n_groups) stage(grp + 1, s_tab + ((grp + 1) & 1) * p.stage_floats);
             int sm_off = 0;
-            for (int pp = p0; pp < p1; ++pp) {
-                const int npd = p.npad[pp];
-                const float4* src =
-                    reinterpret_cast<const float4*>(gcc_b + (size_t)p.Nw * p.off[pp] + (size_t)w0 * npd);
-                float4* dst = reinterpret_cast<float4*>(s_tab + sm_off);
-                const int n4 = (wc * npd) >> 2;
-                for (int i = tid; i < n4; i += kThreads) dst[i] = __ldg(src + i);
-                sm_off += wc * npd;
-            }
-            __syncthreads();
-            sm_off = 0;
             for (int pp = p0; pp < p1; ++pp) {
                 const int npd = p.npad[pp];
 #pragma unroll
@@ -73,7 +86,7 @@ __global__ void __launch_bounds__(kThreads, kMaxThreads / kThreads) srp_gather_k
                     const float c1 = 0.5f * fp1 * fm1 * fm2;
                     const float c2 = -0.5f * fp1 * f * fm2;
                     const float c3 = (1.f / 6.f) * fp1 * f * fm1;
-                    const float* t = s_tab + sm_off + i0 - 1;
+                    const float* t = s_cur + sm_off + i0 - 1;
 #pragma unroll
                     for (int w = 0; w < kWc; ++w) {
                         if (w < wc) {
@@ -108,22 +121,24 @@ int launch_t(SrpGatherParams p, int tile, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
         ASW_CUDA_CHECK(cudaFuncSetAttribute(srp_gather_kernel<GPT, kThreads>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kSmemBudget));
         attr_set = true;
     }
     p.tile = tile;
     dim3 grid((p.G + tile - 1) / tile, p.B);
-    srp_gather_kernel<GPT, kThreads><<<grid, kThreads, p.smem_bytes, s>>>(p);
+    p.stage_floats = p.smem_bytes / 4;
+    srp_gather_kernel<GPT, kThreads><<<grid, kThreads, 2 * p.smem_bytes, s>>>(p);
     ASW_LAUNCH_CHECK("srp_gather_kernel");
     return ASW_OK;
 }
 
-// Hypercubes per CTA.  Every CTA stages the mixture's whole GCC table (cost ~ s_eq hypercubes' worth of gathers)
-// and one CTA fits per SM, so the kernel runs in ceil(CTAs / 148) rounds of (s_eq + tile): pick the tile that
-// minimises it -- e.g. G = 21181, B = 32: 2048 -> 352 CTAs = 2.4 rounds, 1632 -> 416 CTAs = 2.8 rounds.
+// Hypercubes per CTA.  Every CTA stages the mixture's whole GCC table; the copy is asynchronous, but its shared-memory
+// writes compete with the gathers (~s_eq hypercubes' worth of wavefronts), and one CTA fits per SM, so the kernel runs
+// in ceil(CTAs / 148) rounds of (s_eq + tile): pick the tile that minimises it -- e.g. G = 21181, B = 32:
+// 2048 -> 352 CTAs = 2.4 rounds, 1632 -> 416 CTAs = 2.8 rounds.
 int choose_tile(int G, int B, int P, int tab_len) {
     const int kMinTile = 512, kMaxTile = 2 * kMaxThreads;
-    const double s_eq = 0.2 * (double)tab_len / (double)(P > 0 ? P : 1);
+    const double s_eq = 0.12 * (double)tab_len / (double)(P > 0 ? P : 1);
     int best_tile = kMaxTile;
     double best_cost = 1e300;
     for (int nt = (G + kMaxTile - 1) / kMaxTile; nt <= (G + kMinTile - 1) / kMinTile; ++nt) {
