@@ -230,6 +230,8 @@ def run_b200(args, rank, world):
     maps = [torch.empty((B, G), device=dev) for _ in range(2)]     # step i+1 scores while step i is pruned
     map_free = [None, None]
 
+    stage_events = []
+
     def compute(src, events=None, to_host=False):
         """One step: score -> top-K -> peak picking -> greedy patch selection -> shift table -> shift-stack.
         With three streams the stages of consecutive steps software-pipeline (every step still consumes its
@@ -248,6 +250,10 @@ def run_b200(args, rank, world):
         step_no[0] += 1
         if map_free[slot] is not None:
             main.wait_event(map_free[slot])              # prune of step i-2 is done with this map buffer
+        if events is not None and stack_stream is None:   # single-stream pass: stage boundaries for the `stages` object
+            st_ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            st_ev[0].record(main)
+            stage_events.append(st_ev)
         m, val, idx = fe.score(src, out=maps[slot])
         if world > 1:          # the one collective of the path: every rank learns every mixture's top-K
             ps = (step_no[0] - 1) % NPACK
@@ -268,6 +274,8 @@ def run_b200(args, rank, world):
         sstream = main if serial else stack_stream
         scored = torch.cuda.Event()
         scored.record(main)
+        if events is not None and serial:
+            stage_events[-1][1].record(main)
         pstream.wait_event(scored)
         with torch.cuda.stream(pstream):
             shifts_dev, mi_dev, ntot_dev = tables[slot]
@@ -288,12 +296,16 @@ def run_b200(args, rank, world):
                 idx_pin.copy_(idx, non_blocking=True)
             pruned = torch.cuda.Event()
             pruned.record(pstream)
+            if events is not None and serial:
+                stage_events[-1][2].record(pstream)
             map_free[slot] = pruned
         sstream.wait_event(pruned)
         with torch.cuda.stream(sstream):
             fe.stack_counted(src, shifts_dev, mi_dev, ntot_dev, cap, events=events)
             table_free[slot] = torch.cuda.Event()
             table_free[slot].record(sstream)
+            if events is not None and serial:
+                stage_events[-1][3].record(sstream)
 
     def join_streams():
         nonlocal stack_stream
@@ -403,6 +415,10 @@ def run_b200(args, rank, world):
     full = [(t, by) for t, by in zip(k_ms, k_bytes) if by == 4.0 * fe.net_batch * M * T] or list(zip(k_ms, k_bytes))
     k_avg_ms = sum(t for t, _ in full) / len(full)
     k_avg_bytes = sum(by for _, by in full) / len(full)
+    st = stage_events[1:] or stage_events                           # stage times of the serial pass (first step dropped)
+    score_ms = sum(e[0].elapsed_time(e[1]) for e in st) / len(st)
+    prune_ms = sum(e[1].elapsed_time(e[2]) for e in st) / len(st)
+    stack_ms = sum(e[2].elapsed_time(e[3]) for e in st) / len(st)
     # end to end from pinned host memory
     timed_e2e(2)
     ms_e2e = timed_e2e(args.steps)
@@ -444,6 +460,11 @@ def run_b200(args, rank, world):
         "roofline": {"kernel": "shift_stack_vec_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "peak_kind": pk_kind + " (copy, burst)",
                      "algorithmic_bytes_per_launch": k_avg_bytes, "avg_launch_ms": k_avg_ms, "traffic": None},
+        "stages": {"note": "per GPU, from a single-stream pass (stages not overlapped); SURVEY 8(d) stage metrics",
+                   "srp_score_ms": score_ms, "prune_ms": prune_ms, "shift_stack_ms": stack_ms,
+                   "srp_hypercubes_per_s": B * G / (score_ms / 1e3),
+                   "patches_stacked_per_s": N / (stack_ms / 1e3),
+                   "shift_stack_frac_of_nominal_8tbs": achieved / 8000.0},
         "clocks": clocks,
     }
     tp = os.path.join(ROOT, "profiles", "traffic.json")

@@ -120,6 +120,25 @@ def test_max_avg_power_and_si_sdr():
     assert 15 < local_utils.si_sdr(y, x) < 25
 
 
+def test_si_sdr_from_gram_matches_direct():
+    """The Gram-matrix form used by the device fine stage (spot.si_sdr_from_gram) against eval_utils' definition,
+    around the -4 dB clustering threshold and far from it; and Patch.center_pos with a device-supplied centre."""
+    from acousticswarms_speech_b200.patch import Patch
+    from acousticswarms_speech_b200.spot import si_sdr_from_gram
+    rng = np.random.default_rng(5)
+    ref = rng.standard_normal(144000).astype(np.float32)
+    for noise in (0.01, 0.3, 1.0, 1.6, 3.0, 30.0):
+        est = (0.7 * ref + noise * rng.standard_normal(ref.shape[0])).astype(np.float32)
+        want = local_utils.si_sdr(est, ref)
+        e, r = est.astype(np.float64), ref.astype(np.float64)
+        got = si_sdr_from_gram(e @ e, r @ r, e @ r)
+        assert abs(got - want) < 1e-3, (noise, got, want)
+    p = Patch(np.zeros(3, dtype=np.int64), np.full(3, 4), None, None, area_fn=lambda: np.ones((3, 5)),
+              centre=np.array([1.0, 2.0, 3.0]))
+    assert np.array_equal(p.center_pos(), [1.0, 2.0, 3.0]) and p._area_points is None
+    assert p.area_size() == 5 and np.array_equal(p.area_points_getter()(), np.ones((3, 5)))
+
+
 def test_weight_mean_and_merge_center():
     mic = synth.small_scene(4, 2).mic_positions
     pts = np.stack(np.meshgrid(np.linspace(0.8, 1.2, 9), np.linspace(-0.2, 0.2, 9), [0.3], indexing="ij"), 0).reshape(3, -1)
