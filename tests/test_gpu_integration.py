@@ -368,6 +368,47 @@ def test_device_powers_give_the_host_loop_results(cuda_device, desk):
         assert np.abs(a[1] - b[1]).max() <= 1e-7 and abs(a[2] - b[2]) <= 1e-5 * b[2]
 
 
+def test_c3_shape_fine_refinement_over_a_batch(cuda_device, desk):
+    """BASELINE configs[2] in small: several mixtures -> device pruning -> every kept candidate of every mixture
+    subdivided in ONE asw_subdivide launch -> fine + centre patches of the whole batch through one fused
+    shift-stack + normalize_input.  Fine lists against the host mirror of search_area; sampled stacked rows against
+    the oracle's shift / normalize_input restatement (network.py:75-83, SpeakerLocalization/network.py:28-40)."""
+    import copy
+    from acousticswarms_speech_b200 import local_utils, native
+    from acousticswarms_speech_b200.pipeline import FrontEnd
+    g, scene, mix, ma = desk
+    fe = FrontEnd(ma.SRP_node)
+    mixes = np.stack([mix, synth.mixture(scene, 5, mix.shape[1], seed=61), synth.mixture(scene, 3, mix.shape[1], seed=62)])
+    mix_dev = torch.from_numpy(mixes).cuda()
+    coarse = fe.prune(fe.score(mix_dev)[0])
+    cands, owner = [], []
+    for b, pl in enumerate(coarse):
+        for p in pl[:5]:
+            cands.append(p)
+            owner.append(b)
+    host_c = copy.deepcopy(cands)
+    for c in host_c:
+        c.area_points
+    fine = ma._search_area_device(cands)                      # all mixtures' candidates, one launch
+    want = [local_utils.search_area([c], scene.mic_positions, ma.upper_bound_pairwise) for c in host_c]
+    per_mixture = [[] for _ in range(mixes.shape[0])]
+    for b, fl, wl in zip(owner, fine, want):
+        assert [list(p.sample_offset) for p in fl] == [list(p.sample_offset) for p in wl]
+        assert [list(p.width_list) for p in fl] == [list(p.width_list) for p in wl]
+        per_mixture[b].extend(fl)
+    shifts, mi = fe.patch_table(per_mixture)
+    assert shifts.shape[0] == sum(len(f) for f in fine) > 100
+    out, means, stds = native.shift_stack_norm(mix_dev, torch.from_numpy(shifts).cuda(), torch.from_numpy(mi).cuda())
+    out, means, stds = out.cpu().numpy(), means.cpu().numpy(), stds.cpu().numpy()
+    rng = np.random.default_rng(0)
+    for n in rng.choice(shifts.shape[0], 12, replace=False):
+        stacked = shift_oracle.roll_by_gather(mixes[mi[n]], -shifts[n].astype(np.int64))[None]
+        dn, mu, sd = shift_oracle.normalize_input(stacked)
+        assert abs(means[n, 0, 0] - mu[0, 0, 0]) <= 1e-6 * max(1.0, abs(mu[0, 0, 0]))
+        assert abs(stds[n, 0, 0] - sd[0, 0, 0]) <= 1e-5 * sd[0, 0, 0]
+        assert np.abs(out[n] - dn[0]).max() <= TOL * np.abs(dn[0]).max()
+
+
 def test_two_mic_array_end_to_end(cuda_device):
     """M = 2: one pair, one TDoA dimension -- exercises D = 1 in scoring, peak picking and patch selection."""
     from acousticswarms_speech_b200.mic_array import Mic_Array
