@@ -363,6 +363,11 @@ int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len,
         set_error("asw_srp_score: B=%d exceeds the grid limit 65535; split the batch", B);
         return ASW_ERR_ARG;
     }
+    DeviceGuard guard(h->device);
+    if (!guard.ok) {
+        set_error("asw_srp_score: cannot make device %d current", h->device);
+        return ASW_ERR_CUDA;
+    }
     cudaStream_t s = (cudaStream_t)stream;
     const int Nw = asw_srp_num_windows(T, win_len);
     const int Nf = asw_srp_num_frames_mode(win_len, h->nfft, h->hop, h->frame_mode);
@@ -467,6 +472,7 @@ int asw_srp_read_cc(asw_srp_t* h, float* cc_dev, void* stream) {
         set_error("asw_srp_read_cc: null argument");
         return ASW_ERR_ARG;
     }
+    DeviceGuard guard(h->device);
     const size_t n = (size_t)h->last_B * h->last_Nw * h->F * h->P;
     if (n == 0) return ASW_OK;
     ASW_CUDA_CHECK(cudaMemcpyAsync(cc_dev, h->d_cc, n * sizeof(float2), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -493,6 +499,7 @@ int asw_srp_read_gcc(asw_srp_t* h, float* gcc_dev, void* stream) {
         set_error("asw_srp_read_gcc: null argument");
         return ASW_ERR_ARG;
     }
+    DeviceGuard guard(h->device);
     const size_t n = (size_t)h->last_B * h->last_Nw * h->tab_len;
     if (n == 0) return ASW_OK;
     ASW_CUDA_CHECK(cudaMemcpyAsync(gcc_dev, h->d_gcc, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));

@@ -39,6 +39,34 @@ void count_launch(int n = 1);
         asw::count_launch();                                                        \
     } while (0)
 
+// Makes a handle's device current for the duration of an entry point (and restores the caller's).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) { ok = false; return; }
+        if (cur != dev) {
+            ok = cudaSetDevice(dev) == cudaSuccess;
+            if (ok) prev = cur;
+        }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// cudaFuncSetAttribute is per device: true the first time a kernel is configured on the current device.
+struct PerDeviceOnce {
+    unsigned long long mask = 0;
+    bool need() {
+        int d = 0;
+        cudaGetDevice(&d);
+        const unsigned long long bit = 1ull << (d & 63);
+        const bool first = !(mask & bit);
+        mask |= bit;
+        return first;
+    }
+};
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }

@@ -227,10 +227,9 @@ int launch_gcc(const GccParams& p, cudaStream_t s) {
     if (p.tw1024 && p.twpost && p.max_int_lags <= kTileFloats && p.max_int_lags <= kNfft && p.bin0 + p.F <= kNc) {
         dim3 grid((p.P + kFftWarps - 1) / kFftWarps, p.Nw, p.B);
         const size_t smem = (size_t)kFftWarps * (kTileFloats + 2 * kMaxBins) * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceOnce attr_once;
+        if (attr_once.need()) {
             ASW_CUDA_CHECK(cudaFuncSetAttribute(gcc_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
         }
         gcc_fft_kernel<<<grid, 32 * kFftWarps, smem, s>>>(p);
         ASW_LAUNCH_CHECK("gcc_fft_kernel");

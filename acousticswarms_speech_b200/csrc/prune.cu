@@ -214,6 +214,7 @@ int asw_peaks_find(asw_peaks_t* h, const float* map_dev, int B, int32_t* peaks_d
         set_error("asw_peaks_find: B=%d exceeds the grid limit 65535; split the batch", B);
         return ASW_ERR_ARG;
     }
+    DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
     if (B > h->Bcap) {
         if (h->d_first) cudaFree(h->d_first);

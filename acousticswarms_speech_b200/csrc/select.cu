@@ -900,6 +900,7 @@ int asw_select_patches(asw_select_t* h, const float* map_dev, const int32_t* pea
         set_error("asw_select_patches: null argument or bad shape");
         return ASW_ERR_ARG;
     }
+    DeviceGuard guard(h->device);
     SelectParams p{};
     p.peaks = peaks_dev;
     p.count = count_dev;
@@ -962,6 +963,7 @@ int asw_subdivide(asw_select_t* h, const int32_t* centres_dev, const int32_t* wi
         return ASW_ERR_RANGE;
     }
     if (n == 0) return ASW_OK;
+    DeviceGuard guard(h->device);
     const size_t need = (size_t)n * 3 * kListCap;
     if (need > h->lists_cap) {
         if (h->d_lists) cudaFree(h->d_lists);
@@ -991,10 +993,9 @@ int asw_subdivide(asw_select_t* h, const int32_t* centres_dev, const int32_t* wi
     q.root_after = root_after_dev;
     q.status = status_dev;
     const size_t smem = 2 * (size_t)kMaxNodes * sizeof(SubNode);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
         ASW_CUDA_CHECK(cudaFuncSetAttribute(subdivide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     subdivide_kernel<<<n, kSubThreads, smem, (cudaStream_t)stream>>>(q);
     ASW_LAUNCH_CHECK("subdivide_kernel");

@@ -118,11 +118,10 @@ __global__ void __launch_bounds__(kThreads, kMaxThreads / kThreads) srp_gather_k
 
 template <int GPT, int kThreads>
 int launch_t(SrpGatherParams p, int tile, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
         ASW_CUDA_CHECK(cudaFuncSetAttribute(srp_gather_kernel<GPT, kThreads>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kSmemBudget));
-        attr_set = true;
     }
     p.tile = tile;
     dim3 grid((p.G + tile - 1) / tile, p.B);

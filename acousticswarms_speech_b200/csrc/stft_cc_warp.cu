@@ -205,8 +205,8 @@ size_t warp_smem_bytes(int F) {
 template <int M>
 int launch_t(const StftCcParams& p, cudaStream_t s) {
     const size_t smem = warp_smem_bytes<M>(p.F);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
         ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_warp_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)warp_smem_bytes<M>(200)));
         // without this the driver may pick a carve-out that fits only one CTA (ncu: occupancy limit 1)
@@ -215,7 +215,6 @@ int launch_t(const StftCcParams& p, cudaStream_t s) {
         int pct = (int)((ctas * (warp_smem_bytes<M>(200) + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
         if (pct > 100) pct = 100;
         ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_warp_kernel<M>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-        attr_set = true;
     }
     dim3 grid(p.NG, p.Nw, p.B);
     stft_cc_warp_kernel<M><<<grid, 32 * M, smem, s>>>(p);

@@ -306,8 +306,9 @@ def build_shift_table(n_patches, offsets, capacity, shifts=None, mix_index=None,
         mix_index = torch.zeros((capacity,), device=dev, dtype=torch.int32)
     if n_total is None:
         n_total = torch.zeros((1,), device=dev, dtype=torch.int32)
-    _lib.check(_lib.load().asw_build_shift_table(_ptr(n_patches), _ptr(offsets), B, max_patches, D, _ptr(shifts),
-                                                 _ptr(mix_index), _ptr(n_total), int(capacity), _stream(dev)))
+    with torch.cuda.device(offsets.device):     # handle-less entry points launch on the current device
+        _lib.check(_lib.load().asw_build_shift_table(_ptr(n_patches), _ptr(offsets), B, max_patches, D, _ptr(shifts),
+                                                     _ptr(mix_index), _ptr(n_total), int(capacity), _stream(dev)))
     return shifts, mix_index, n_total
 
 
@@ -323,8 +324,9 @@ def shift_stack_counted(mix, shifts, mix_index, n_total, n_base, N, out):
     B, M, T = mix.shape
     if shifts.shape[1] != M or out.numel() < N * M * T:
         raise _lib.AswError("shift table / output shape mismatch")
-    _lib.check(_lib.load().asw_shift_stack_counted(_ptr(mix), _ptr(shifts), _ptr(mix_index), _ptr(n_total), int(n_base),
-                                                   int(N), B, M, T, _ptr(out), _stream(mix.device)))
+    with torch.cuda.device(mix.device):     # handle-less entry points launch on the current device
+        _lib.check(_lib.load().asw_shift_stack_counted(_ptr(mix), _ptr(shifts), _ptr(mix_index), _ptr(n_total), int(n_base),
+                                                       int(N), B, M, T, _ptr(out), _stream(mix.device)))
     return out
 
 
@@ -336,8 +338,9 @@ def map_topk(srp_map, K, idx_offset=0):
     B, G = srp_map.shape
     val = torch.empty((B, K), device=srp_map.device, dtype=torch.float32)
     idx = torch.empty((B, K), device=srp_map.device, dtype=torch.int32)
-    _lib.check(_lib.load().asw_map_topk(_ptr(srp_map), B, G, int(K), int(idx_offset), _ptr(val), _ptr(idx),
-                                        _stream(srp_map.device)))
+    with torch.cuda.device(srp_map.device):     # handle-less entry points launch on the current device
+        _lib.check(_lib.load().asw_map_topk(_ptr(srp_map), B, G, int(K), int(idx_offset), _ptr(val), _ptr(idx),
+                                            _stream(srp_map.device)))
     return val, idx
 
 
@@ -363,8 +366,9 @@ def shift_stack(mix, shifts, mix_index=None, out=None):
             raise _lib.AswError("out is too small")
     if N == 0:
         return out[:0]
-    _lib.check(_lib.load().asw_shift_stack(_ptr(mix), _ptr(shifts), _ptr(mix_index) if mix_index is not None else None,
-                                           N, B, M, T, _ptr(out), _stream(mix.device)))
+    with torch.cuda.device(mix.device):     # handle-less entry points launch on the current device
+        _lib.check(_lib.load().asw_shift_stack(_ptr(mix), _ptr(shifts), _ptr(mix_index) if mix_index is not None else None,
+                                               N, B, M, T, _ptr(out), _stream(mix.device)))
     return out[:N]
 
 
@@ -390,10 +394,11 @@ def shift_stack_norm(mix, shifts, mix_index=None, out=None):
     work = torch.empty((N, 2), device=mix.device, dtype=torch.float64)
     if N == 0:
         return out[:0], means.view(0, 1, 1), stds.view(0, 1, 1)
-    _lib.check(_lib.load().asw_shift_stack_norm(_ptr(mix), _ptr(shifts),
-                                                _ptr(mix_index) if mix_index is not None else None, N, B, M, T,
-                                                _ptr(out), _ptr(means), _ptr(stds), _ptr(work),
-                                                _stream(mix.device)))
+    with torch.cuda.device(mix.device):     # handle-less entry points launch on the current device
+        _lib.check(_lib.load().asw_shift_stack_norm(_ptr(mix), _ptr(shifts),
+                                                    _ptr(mix_index) if mix_index is not None else None, N, B, M, T,
+                                                    _ptr(out), _ptr(means), _ptr(stds), _ptr(work),
+                                                    _stream(mix.device)))
     return out[:N], means.view(N, 1, 1), stds.view(N, 1, 1)
 
 
@@ -407,7 +412,8 @@ def pcm16_to_f32(pcm, out=None):
         if out.numel() != pcm.numel():
             raise _lib.AswError("out must have as many elements as pcm")
     if pcm.numel():
-        _lib.check(_lib.load().asw_pcm16_to_f32(_ptr(pcm), _ptr(out), pcm.numel(), _stream(pcm.device)))
+        with torch.cuda.device(pcm.device):     # handle-less entry points launch on the current device
+            _lib.check(_lib.load().asw_pcm16_to_f32(_ptr(pcm), _ptr(out), pcm.numel(), _stream(pcm.device)))
     return out
 
 
@@ -424,8 +430,9 @@ def patch_powers(x, window=12000, demean=True):
     maxavg = torch.empty((N,), device=x.device, dtype=torch.float32)
     arg = torch.empty((N,), device=x.device, dtype=torch.int32)
     if N:
-        _lib.check(_lib.load().asw_patch_powers(_ptr(x), N, T, int(window), int(bool(demean)), _ptr(mean), _ptr(power),
-                                                _ptr(maxavg), _ptr(arg), _stream(x.device)))
+        with torch.cuda.device(x.device):     # handle-less entry points launch on the current device
+            _lib.check(_lib.load().asw_patch_powers(_ptr(x), N, T, int(window), int(bool(demean)), _ptr(mean), _ptr(power),
+                                                    _ptr(maxavg), _ptr(arg), _stream(x.device)))
     return mean, power, maxavg, arg
 
 
