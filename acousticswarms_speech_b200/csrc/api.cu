@@ -32,6 +32,7 @@ struct asw_srp {
     int nfft = 0, hop = 0, bin0 = 0, bin1 = 0, F = 0, U = 0;
     float tol = 0.f;
     int frame_mode = ASW_FRAMES_FLOOR;
+    int stft_path = ASW_STFT_AUTO;
     // per-pair lag-table layout (host copies) and device mirrors
     std::vector<int> lag_lo, n_entries, npad, off;
     int tab_len = 0;
@@ -48,6 +49,8 @@ struct asw_srp {
     // workspace (grown on demand)
     float2* d_cc_part = nullptr;
     size_t cc_part_cap = 0;
+    float2* d_px = nullptr;       // [B][Nw][Nf][M][F] spectra of the split STFT path
+    size_t px_cap = 0;
     float2* d_cc = nullptr;
     size_t cc_cap = 0;
     float* d_gcc = nullptr;
@@ -164,6 +167,15 @@ int asw_srp_num_frames_mode(int win_len, int nfft, int hop, int frame_mode) {
     if (win_len < 1 || hop <= 0) return 0;
     if (win_len < nfft) return 1;                                  // one frame, zero padded
     return (win_len - nfft + hop - 1) / hop + 1;
+}
+
+int asw_srp_set_stft_path(asw_srp_t* h, int path) {
+    if (!h || path < ASW_STFT_AUTO || path > ASW_STFT_GENERIC) {
+        set_error("asw_srp_set_stft_path: null handle or unknown path %d", path);
+        return ASW_ERR_ARG;
+    }
+    h->stft_path = path;
+    return ASW_OK;
 }
 
 int asw_srp_set_frame_mode(asw_srp_t* h, int frame_mode) {
@@ -343,6 +355,7 @@ int asw_srp_destroy(asw_srp_t* h) {
     cudaFree(h->d_off);
     cudaFree(h->d_pos);
     cudaFree(h->d_perm);
+    cudaFree(h->d_px);
     cudaFree(h->d_tw1024);
     cudaFree(h->d_twpost);
     cudaFree(h->d_fir);
@@ -414,7 +427,20 @@ int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len,
     if ((rc = ensure(&h->d_gcc, &h->gcc_cap, (size_t)B * Nw * h->tab_len)) != ASW_OK) return rc;
 
     sp.cc_part = h->d_cc_part;
-    if ((rc = fast ? launch_stft_cc_warp(sp, s) : launch_stft_cc(sp, s)) != ASW_OK) return rc;
+    // fused register kernel for M <= 8; beyond that (or on request) spectra go through global memory to a pair kernel;
+    // the radix-4 shared-memory kernel remains as the fallback for bin ranges the warp FFT does not cover
+    const bool split = stft_split_supported(sp) &&
+                       (h->stft_path == ASW_STFT_SPLIT || (h->stft_path == ASW_STFT_AUTO && !fast));
+    if (split) {
+        if ((rc = ensure(&h->d_px, &h->px_cap, (size_t)B * Nw * Nf * h->M * h->F)) != ASW_OK) return rc;
+        sp.px_out = h->d_px;
+        rc = launch_stft_split(sp, s);
+    } else if (fast && h->stft_path != ASW_STFT_GENERIC) {
+        rc = launch_stft_cc_warp(sp, s);
+    } else {
+        rc = launch_stft_cc(sp, s);
+    }
+    if (rc != ASW_OK) return rc;
 
     GccParams gp{};
     gp.cc_part = h->d_cc_part;

@@ -78,6 +78,7 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(
 struct StftCcParams {
     const float* mix;      // [B][M][T]
     float2* cc_part;       // [B][Nw][NG][P][F]  (bin fastest: coalesced for the writer and for gcc.cu)
+    float2* px_out;        // [B][Nw][Nf][M][F] PHAT-normalised spectra (split path only, else null)
     const float2* tw1024;  // [1024]  exp(-2 pi i t / 1024)
     const float2* twpost;  // [F]     exp(-2 pi i k / 2048), k = bin0 + f
     int B, M, T, Nw, step, Nf, NG, FG, bin0, F, P;
@@ -88,6 +89,8 @@ int launch_stft_cc(const StftCcParams& p, cudaStream_t s);          // generic (
 bool stft_cc_warp_supported(const StftCcParams& p);                  // fast path: M <= 8, bins in [1, 224)
 int stft_cc_warp_ctas_per_sm(int M);
 int launch_stft_cc_warp(const StftCcParams& p, cudaStream_t s);
+bool stft_split_supported(const StftCcParams& p);                    // FFT + PHAT to global, then pair products: any M <= 32
+int launch_stft_split(const StftCcParams& p, cudaStream_t s);
 
 struct GccParams {
     const float2* cc_part;  // [B][Nw][NG][P][F]

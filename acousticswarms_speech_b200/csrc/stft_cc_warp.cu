@@ -76,7 +76,11 @@ struct Cfg {
     static constexpr int kFmax = kThreads * kNb;
 };
 
-template <int M>
+// SPLIT = false (M <= 8): warp m = mic m, pair products accumulated in registers, one partial cross-spectrum per CTA.
+// SPLIT = true  (any M <= 32): the CTA's M_ = 8 warps take 8 mics of a chunk (blockIdx.z = b * chunks + chunk), the
+// PHAT-normalised spectra go to global memory as pX[b][w][frame][mic][bin] and pair_products_kernel forms the
+// cross-spectra: M(M-1)/2 accumulators per bin do not fit next to an FFT in registers beyond 8 mics.
+template <int M, bool SPLIT>
 // no __launch_bounds__ here: it would override the per-file -maxrregcount=128 (see build.py)
 __global__ void stft_cc_warp_kernel(StftCcParams p) {
     using C = Cfg<M>;
@@ -85,9 +89,12 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
     float* tile = smem + (threadIdx.x >> 5) * (2 * 32 * 33);
     float2* s_px = reinterpret_cast<float2*>(smem + M * (2 * 32 * 33));
     const int lane = threadIdx.x & 31;
-    const int m = threadIdx.x >> 5;  // this warp's mic
     const int tid = threadIdx.x;
-    const int grp = blockIdx.x, w = blockIdx.y, b = blockIdx.z;
+    const int grp = blockIdx.x, w = blockIdx.y;
+    const int mchunks = SPLIT ? (p.M + M - 1) / M : 1;
+    const int b = SPLIT ? blockIdx.z / mchunks : blockIdx.z;
+    const int m = (SPLIT ? (blockIdx.z % mchunks) * M : 0) + (threadIdx.x >> 5);  // this warp's mic
+    if (SPLIT && m >= p.M) return;   // whole warp; the split path has no block-wide barrier
     const int F = p.F;
     const float tol2 = p.tol * p.tol;
 
@@ -97,11 +104,11 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
     const float2 w16 = __ldg(p.tw1024 + ((16 * lane) & 1023));
     const float2 w24 = __ldg(p.tw1024 + ((24 * lane) & 1023));
 
-    c64 acc[C::kNb][C::kP];   // packed (re, im): the pair products run on FFMA2 / FADD2
+    c64 acc[SPLIT ? 1 : C::kNb][SPLIT ? 1 : C::kP];   // packed (re, im): the pair products run on FFMA2 / FADD2
 #pragma unroll
-    for (int i = 0; i < C::kNb; ++i)
+    for (int i = 0; i < (SPLIT ? 1 : C::kNb); ++i)
 #pragma unroll
-        for (int q = 0; q < C::kP; ++q) acc[i][q] = pk(0.f, 0.f);
+        for (int q = 0; q < (SPLIT ? 1 : C::kP); ++q) acc[i][q] = pk(0.f, 0.f);
 
     const int n0 = grp * p.FG;
     const int n1 = min(p.Nf, n0 + p.FG);
@@ -113,7 +120,8 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
     if (n0 < n1) prefetch_frame_n(tile, xm, n0, p.win_len, lane);
 
     for (int n = n0; n < n1; ++n) {
-        float2* px = s_px + (size_t)(n & 1) * M * F;
+        float2* px = SPLIT ? p.px_out + ((((size_t)b * p.Nw + w) * p.Nf + n) * p.M) * F
+                           : s_px + (size_t)(n & 1) * M * F;
         {
             c64 v[32];
             cp_async_wait_all();
@@ -157,6 +165,7 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
                 }
             }
         }
+        if (SPLIT) continue;
         __syncthreads();  // all M mics of frame n are in px
 #pragma unroll
         for (int i = 0; i < C::kNb; ++i) {
@@ -182,6 +191,7 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
         // no second barrier: frame n+1 writes the other px buffer, and frame n+2 reuses this one only
         // after the barrier of frame n+1, which every thread reaches after finishing these reads
     }
+    if (SPLIT) return;
     float2* cc_out = p.cc_part + ((((size_t)b * p.Nw + w) * p.NG + grp) * (size_t)F) * p.P;
 #pragma unroll
     for (int i = 0; i < C::kNb; ++i) {
@@ -191,6 +201,61 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
             for (int q = 0; q < C::kP; ++q) cc_out[(size_t)q * F + f] = upk(acc[i][q]);   // [pair][bin]: coalesced
         }
     }
+}
+
+// Cross-spectra from the stored spectra (split path).  The M(M-1)/2 pairs are covered by tiles of 4 first mics x 8
+// second mics (i in [i0, i0+4), j in [j0, j0+8), j0 = i0, i0+8, ...): a thread owns one bin, keeps the tile's 32
+// accumulators in registers and loads 12 spectra per frame.  CTA = (frame group, window, mixture x tile).
+// Same products, same fused adds and the same frame order as the register path, so M <= 8 gives the same bits either way.
+constexpr int kPairThreads = 256;
+constexpr int kTileI = 4, kTileJ = 8, kMaxPairTiles = 24;   // M = 32: 8 i-blocks x <= 4 j-blocks, 20 tiles
+
+struct PairTiles {
+    int n;
+    unsigned char i0[kMaxPairTiles], j0[kMaxPairTiles];
+};
+
+__global__ void __launch_bounds__(kPairThreads) pair_products_kernel(StftCcParams p, PairTiles tiles) {
+    const int grp = blockIdx.x, w = blockIdx.y;
+    const int t = blockIdx.z % tiles.n, b = blockIdx.z / tiles.n;
+    const int i0 = tiles.i0[t], j0 = tiles.j0[t];
+    const int f = threadIdx.x, F = p.F, M = p.M;
+    if (f >= F) return;
+    c64 acc[kTileI][kTileJ];
+#pragma unroll
+    for (int a = 0; a < kTileI; ++a)
+#pragma unroll
+        for (int c = 0; c < kTileJ; ++c) acc[a][c] = pk(0.f, 0.f);
+    const int n0 = grp * p.FG, n1 = min(p.Nf, n0 + p.FG);
+    for (int n = n0; n < n1; ++n) {
+        const float2* px = p.px_out + ((((size_t)b * p.Nw + w) * p.Nf + n) * M) * F + f;
+        c64 ai[kTileI], ai_rot[kTileI];
+        float2 aj[kTileJ];
+#pragma unroll
+        for (int a = 0; a < kTileI; ++a) {
+            const float2 v = (i0 + a < M) ? px[(size_t)(i0 + a) * F] : make_float2(0.f, 0.f);
+            ai[a] = pk(v.x, v.y);
+            ai_rot[a] = pk(v.y, -v.x);
+        }
+#pragma unroll
+        for (int c = 0; c < kTileJ; ++c) aj[c] = (j0 + c < M) ? px[(size_t)(j0 + c) * F] : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < kTileI; ++a)
+#pragma unroll
+            for (int c = 0; c < kTileJ; ++c)
+                if (i0 + a < j0 + c && j0 + c < M) {
+                    const c64 u = fma2(ai[a], pk(aj[c].x, aj[c].x), mul2(ai_rot[a], pk(aj[c].y, aj[c].y)));
+                    acc[a][c] = add2(acc[a][c], u);
+                }
+    }
+    float2* cc_out = p.cc_part + ((((size_t)b * p.Nw + w) * p.NG + grp) * (size_t)F) * p.P;
+#pragma unroll
+    for (int a = 0; a < kTileI; ++a)
+#pragma unroll
+        for (int c = 0; c < kTileJ; ++c) {
+            const int i = i0 + a, j = j0 + c;
+            if (i < j && j < M) cc_out[(size_t)(i * M - i * (i + 1) / 2 + (j - i - 1)) * F + f] = upk(acc[a][c]);
+        }
 }
 
 }  // namespace
@@ -207,17 +272,17 @@ int launch_t(const StftCcParams& p, cudaStream_t s) {
     const size_t smem = warp_smem_bytes<M>(p.F);
     static PerDeviceOnce attr_once;
     if (attr_once.need()) {
-        ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_warp_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_warp_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)warp_smem_bytes<M>(200)));
         // without this the driver may pick a carve-out that fits only one CTA (ncu: occupancy limit 1)
         // just enough shared memory for the resident CTAs, the rest stays L1
         const int ctas = stft_cc_warp_ctas_per_sm(M);
         int pct = (int)((ctas * (warp_smem_bytes<M>(200) + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
         if (pct > 100) pct = 100;
-        ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_warp_kernel<M>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_warp_kernel<M, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     dim3 grid(p.NG, p.Nw, p.B);
-    stft_cc_warp_kernel<M><<<grid, 32 * M, smem, s>>>(p);
+    stft_cc_warp_kernel<M, false><<<grid, 32 * M, smem, s>>>(p);
     ASW_LAUNCH_CHECK("stft_cc_warp_kernel");
     return ASW_OK;
 }
@@ -235,6 +300,43 @@ int stft_cc_warp_ctas_per_sm(int M) {
     const int by_smem = (int)((227 * 1024) / (M * (2 * 32 * 33) * sizeof(float) + 2 * M * 200 * sizeof(float2) + 1024));
     const int n = by_regs < by_smem ? by_regs : by_smem;
     return n < 1 ? 1 : n;
+}
+
+bool stft_split_supported(const StftCcParams& p) {
+    return p.M >= 2 && p.M <= kMaxMics && p.F <= 200 && p.F <= kPairThreads && p.bin0 >= 1 && p.bin0 + p.F <= 32 * kK2;
+}
+
+// FFT + PHAT of 8 mics per CTA to p.px_out, then the pair products: any M <= 32.
+int launch_stft_split(const StftCcParams& p, cudaStream_t s) {
+    constexpr int W = 8;
+    if (!p.px_out) {
+        set_error("stft split path: no spectrum workspace");
+        return ASW_ERR_ARG;
+    }
+    const size_t smem = (size_t)W * (2 * 32 * 33) * sizeof(float);
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_warp_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int pct = (int)((2 * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_warp_kernel<W, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
+    const int mchunks = (p.M + W - 1) / W;
+    PairTiles tiles{};
+    for (int i0 = 0; i0 < p.M - 1; i0 += kTileI)
+        for (int j0 = i0; j0 < p.M; j0 += kTileJ) {
+            tiles.i0[tiles.n] = (unsigned char)i0;
+            tiles.j0[tiles.n] = (unsigned char)j0;
+            ++tiles.n;
+        }
+    if ((long long)p.B * mchunks > 65535 || (long long)p.B * tiles.n > 65535) {
+        set_error("stft split path: B=%d x M=%d exceeds the grid limit; split the batch", p.B, p.M);
+        return ASW_ERR_ARG;
+    }
+    stft_cc_warp_kernel<W, true><<<dim3(p.NG, p.Nw, p.B * mchunks), 32 * W, smem, s>>>(p);
+    ASW_LAUNCH_CHECK("stft_cc_warp_kernel(split)");
+    pair_products_kernel<<<dim3(p.NG, p.Nw, p.B * tiles.n), kPairThreads, 0, s>>>(p, tiles);
+    ASW_LAUNCH_CHECK("pair_products_kernel");
+    return ASW_OK;
 }
 
 int launch_stft_cc_warp(const StftCcParams& p, cudaStream_t s) {

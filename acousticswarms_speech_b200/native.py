@@ -75,6 +75,10 @@ class NativeSRP:
         _lib.check(self.lib.asw_srp_set_frame_mode(self._h, 1 if enabled else 0))
         self.pad_tail = bool(enabled)
 
+    def set_stft_path(self, path):
+        """"auto" (fused kernel for <= 8 mics, split beyond), "split" or "generic": see asw_srp_set_stft_path."""
+        _lib.check(self.lib.asw_srp_set_stft_path(self._h, {"auto": 0, "split": 1, "generic": 2}[path]))
+
     def num_frames(self, win_len):
         return int(self.lib.asw_srp_num_frames_mode(int(win_len), n_fft, HOP, 1 if self.pad_tail else 0))
 

@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="mixtures per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stft-path", default="auto", choices=["auto", "split", "generic"],
+                    help="kernels of the STFT + PHAT + cross-spectra stage (auto = fused register kernel for <= 8 mics)")
     ap.add_argument("--streams", type=int, default=3, choices=[1, 3],
                     help="3: scoring (SM/shared-memory bound), pruning (latency bound, B CTAs) and shift-stack (HBM "
                          "bound) of consecutive steps run on their own streams and overlap; 1: fully serial")
@@ -180,6 +182,7 @@ def run_b200(args, rank, world):
     scene = synth.desk_array(N_MICS, np.random.default_rng(GEOM_SEED), FS)
     node = SRP_PHAT(scene.mic_positions, freq_bins, scene.roi, FS=FS, n_fft=n_fft, grid_size=0.05,
                     threshold=list(SRP_THRESHOLDS), WIDTH=8, device=dev)
+    node.native.set_stft_path(args.stft_path)
     fe = FrontEnd(node, dev)
     G = node.grids.shape[0]
     M, T = N_MICS, T_SAMPLES

@@ -80,6 +80,13 @@ int asw_srp_destroy(asw_srp_t* h);
  * 24000-sample windows: 67 vs 68 and 43 vs 44 frames).  A maintainer who can run the pinned package re-pins A1
  * with this one call. */
 enum { ASW_FRAMES_FLOOR = 0, ASW_FRAMES_PAD_TAIL = 1 };
+
+/* Which kernels compute the STFT + PHAT + cross-spectra stage (:404-426); results agree to rounding (FUSED and
+ * SPLIT bit for bit).  AUTO: FUSED for M <= 8, SPLIT for 9..32 mics, GENERIC where neither applies.
+ *   ASW_STFT_SPLIT    warp FFT + PHAT to a [B][Nw][Nf][M][F] spectrum buffer, then a pair-product kernel (any M <= 32)
+ *   ASW_STFT_GENERIC  radix-4 shared-memory FFT with the pair products in the same kernel (any M, any bin range) */
+enum { ASW_STFT_AUTO = 0, ASW_STFT_SPLIT = 1, ASW_STFT_GENERIC = 2 };
+int asw_srp_set_stft_path(asw_srp_t* h, int path);
 int asw_srp_set_frame_mode(asw_srp_t* h, int frame_mode);
 int asw_srp_num_frames_mode(int win_len, int nfft, int hop, int frame_mode);
 

@@ -158,6 +158,37 @@ def test_tail_padded_frame_mode(cuda_device, small, n_mics, T):
     assert torch.equal(a, srp.score(x, w2))
 
 
+def test_split_stft_path(cuda_device, small):
+    """ASW_STFT_SPLIT (spectra through global memory + pair-product kernel): bit-identical to the fused register
+    kernel for M = 4 (same products, same adds, same frame order), and within tolerance of the oracle and of the
+    generic kernel for M = 10 where AUTO selects it."""
+    scene, geo = small
+    x = torch.from_numpy(synth.mixtures(scene, 2, 96000, seeds=[5, 6])).cuda()
+    srp = _native(scene, geo.grids)
+    fused = srp.score(x, 36000).clone()
+    cc_fused = srp.read_cc().clone()
+    srp.set_stft_path("split")
+    split = srp.score(x, 36000).clone()
+    assert torch.equal(srp.read_cc(), cc_fused) and torch.equal(split, fused)
+    srp.set_pad_tail(True)                                  # the ragged last frame through the split path too
+    a = srp.score(x, 36000).clone()
+    srp.set_stft_path("auto")
+    assert torch.equal(a, srp.score(x, 36000))
+
+    scene = synth.table_array(10, np.random.default_rng(4))
+    scene.roi = [2.0, 2.6, 3.2, 3.8, 0.0, 0.4]
+    geo = geometry_oracle.GeometryOracle(scene.mic_positions, scene.roi, build_fine=False)
+    mix = synth.mixture(scene, 2, 48000, seed=3)
+    srp = _native(scene, geo.grids)                         # AUTO -> split for 10 mics
+    got = srp.score(torch.from_numpy(mix).cuda(), 24000).cpu().numpy()[0]
+    want = srp_oracle.score(mix, geo.grids, scene.mic_positions, freq_bins, scene.fs, n_fft)
+    assert np.abs(got - want).max() <= TOL * want.max()
+    srp.set_stft_path("generic")
+    gen = srp.score(torch.from_numpy(mix).cuda(), 24000).cpu().numpy()[0]
+    assert np.abs(gen - want).max() <= TOL * want.max()
+    assert np.abs(gen - got).max() <= 1e-5 * want.max()
+
+
 def test_topk(cuda_device):
     from acousticswarms_speech_b200 import native
     rng = np.random.default_rng(0)
