@@ -411,6 +411,30 @@ def run_b200(args, rank, world):
     timed(max(2, min(args.steps, 5)), events=events)
     stack_stream = saved_stream
     torch.cuda.synchronize()
+    # self-check (untimed): the 3-stream pipeline must produce exactly what the serial schedule produces -- maps,
+    # top-K, peak counts, patch counts, the device-built shift tables and the stacked ring buffers
+    def snapshot(serial):
+        nonlocal stack_stream
+        saved = stack_stream
+        if serial:
+            stack_stream = None
+        out = []
+        for _ in range(2):                                            # both buffer slots
+            slot = step_no[0] & 1
+            compute(mix_dev, to_host=True)
+            join_streams()
+            torch.cuda.synchronize()
+            sh, mi_t, nt = tables[slot]
+            n = int(nt.item())
+            out.append([map_pin.clone(), val_pin.clone(), idx_pin.clone(), count_pin.clone(), sel_pin[:, 0].clone(),
+                        sh[:n].cpu(), mi_t[:n].cpu(), torch.tensor([n]),
+                        torch.stack([bf.view(torch.int32).sum() for bf in fe._bufs]).cpu()])
+        stack_stream = saved
+        return out
+    ref_out, pipe_out = snapshot(True), snapshot(False)
+    selfcheck = all(torch.equal(x, y) for a, b2 in zip(ref_out, pipe_out) for x, y in zip(a, b2))
+    if not selfcheck:
+        raise RuntimeError("bench self-check failed: the pipelined schedule and the serial schedule disagree")
     per = (cap + fe.net_batch - 1) // fe.net_batch                  # launches per step
     valid = [max(0, min(fe.net_batch, N - (j % per) * fe.net_batch)) for j in range(len(events))]
     k_ms = [a.elapsed_time(b) for a, b, _ in events]
@@ -468,6 +492,7 @@ def run_b200(args, rank, world):
                    "srp_hypercubes_per_s": B * G / (score_ms / 1e3),
                    "patches_stacked_per_s": N / (stack_ms / 1e3),
                    "shift_stack_frac_of_nominal_8tbs": achieved / 8000.0},
+        "selfcheck": "pipelined step == serial step (maps, top-K, peak / patch counts, shift tables, stacked ring checksums)",
         "clocks": clocks,
     }
     tp = os.path.join(ROOT, "profiles", "traffic.json")
