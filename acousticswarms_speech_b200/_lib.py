@@ -17,7 +17,7 @@ SYMBOLS = [
     "asw_peaks_create", "asw_peaks_destroy", "asw_peaks_find",
     "asw_select_create", "asw_select_destroy", "asw_select_patches", "asw_subdivide",
     "asw_build_shift_table", "asw_shift_stack_counted", "asw_pcm16_to_f32", "asw_patch_powers",
-    "asw_srp_set_frame_mode", "asw_srp_num_frames_mode", "asw_select_set_grid1", "asw_srp_set_stft_path",
+    "asw_srp_set_frame_mode", "asw_srp_num_frames_mode", "asw_select_set_grid1", "asw_srp_set_stft_path", "asw_srp_gcc", "asw_srp_gather",
 ]
 
 
@@ -69,6 +69,8 @@ def load():
     lib.asw_pcm16_to_f32.argtypes = [vp, vp, c.c_longlong, vp]
     lib.asw_srp_set_frame_mode.argtypes = [vp, i32]
     lib.asw_srp_set_stft_path.argtypes = [vp, i32]
+    lib.asw_srp_gcc.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    lib.asw_srp_gather.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.asw_srp_num_frames_mode.argtypes = [i32, i32, i32, i32]
     lib.asw_patch_powers.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     for name in SYMBOLS:

@@ -367,30 +367,10 @@ int asw_srp_destroy(asw_srp_t* h) {
     return ASW_OK;
 }
 
-int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len, float* map_dev, void* stream) {
-    if (!h || !mix_dev || !map_dev || B < 1) {
-        set_error("asw_srp_score: null handle/buffer or B < 1");
-        return ASW_ERR_ARG;
-    }
-    if (B > 65535) {
-        set_error("asw_srp_score: B=%d exceeds the grid limit 65535; split the batch", B);
-        return ASW_ERR_ARG;
-    }
-    DeviceGuard guard(h->device);
-    if (!guard.ok) {
-        set_error("asw_srp_score: cannot make device %d current", h->device);
-        return ASW_ERR_CUDA;
-    }
-    cudaStream_t s = (cudaStream_t)stream;
-    const int Nw = asw_srp_num_windows(T, win_len);
-    const int Nf = asw_srp_num_frames_mode(win_len, h->nfft, h->hop, h->frame_mode);
-    if (Nw < 1 || Nf < 1) {
-        // no analysis window fits: the reference leaves the map at its zero initialisation (:253)
-        ASW_CUDA_CHECK(cudaMemsetAsync(map_dev, 0, sizeof(float) * (size_t)B * h->G, s));
-        h->last_B = B;
-        h->last_Nw = 0;
-        return ASW_OK;
-    }
+// Stage 1 + 2 of the scoring path: STFT + PHAT + cross-spectra, then the pair GCC lag tables into `gcc_out`
+// ([B][Nw * tab_len], pair-major).  Nw >= 1 and Nf >= 1 are the caller's responsibility.
+static int run_gcc(asw_srp* h, const float* mix_dev, int B, int T, int win_len, int Nw, int Nf, float* gcc_out,
+                   cudaStream_t s) {
     StftCcParams sp{};
     sp.mix = mix_dev;
     sp.tw1024 = h->d_tw1024;
@@ -416,15 +396,9 @@ int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len,
     sp.NG = NG;
     sp.FG = FG;
 
-    const int wc = Nw < srp_gather_windows_per_chunk() ? Nw : srp_gather_windows_per_chunk();
-    if (h->grp_wc != wc) {
-        int rc = build_groups(h, wc);
-        if (rc != ASW_OK) return rc;
-    }
     int rc;
     if ((rc = ensure(&h->d_cc_part, &h->cc_part_cap, (size_t)B * Nw * NG * h->F * h->P)) != ASW_OK) return rc;
     if ((rc = ensure(&h->d_cc, &h->cc_cap, (size_t)B * Nw * h->F * h->P)) != ASW_OK) return rc;
-    if ((rc = ensure(&h->d_gcc, &h->gcc_cap, (size_t)B * Nw * h->tab_len)) != ASW_OK) return rc;
 
     sp.cc_part = h->d_cc_part;
     // fused register kernel for M <= 8; beyond that (or on request) spectra go through global memory to a pair kernel;
@@ -444,7 +418,7 @@ int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len,
 
     GccParams gp{};
     gp.cc_part = h->d_cc_part;
-    gp.gcc = h->d_gcc;
+    gp.gcc = gcc_out;
     gp.cc_out = h->d_cc;
     gp.lag_lo = h->d_lag_lo;
     gp.n_entries = h->d_n_entries;
@@ -468,10 +442,18 @@ int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len,
     gp.tab_len = h->tab_len;
     gp.inv_nf = 1.0f / (float)Nf;
     gp.scale = (float)(1.0 / ((double)h->F * (double)h->P));
-    if ((rc = launch_gcc(gp, s)) != ASW_OK) return rc;
+    return launch_gcc(gp, s);
+}
 
+// Stage 3: steered response of every hypercube of the handle from GCC tables `gcc` ([B][Nw * tab_len]).
+static int run_gather(asw_srp* h, const float* gcc, int B, int Nw, float* map_dev, cudaStream_t s) {
+    const int wc = Nw < srp_gather_windows_per_chunk() ? Nw : srp_gather_windows_per_chunk();
+    if (h->grp_wc != wc) {
+        int rc = build_groups(h, wc);
+        if (rc != ASW_OK) return rc;
+    }
     SrpGatherParams rp{};
-    rp.gcc = h->d_gcc;
+    rp.gcc = gcc;
     rp.pos = h->d_pos;
     rp.npad = h->d_npad;
     rp.off = h->d_off;
@@ -486,11 +468,69 @@ int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len,
     rp.tab_len = h->tab_len;
     rp.n_groups = h->n_groups;
     rp.smem_bytes = h->smem_bytes;
-    if ((rc = launch_srp_gather(rp, s)) != ASW_OK) return rc;
+    return launch_srp_gather(rp, s);
+}
 
+static int check_batch(const char* who, const asw_srp* h, const void* a, const void* b, int B) {
+    if (!h || !a || !b || B < 1) {
+        set_error("%s: null handle/buffer or B < 1", who);
+        return ASW_ERR_ARG;
+    }
+    if (B > 65535) {
+        set_error("%s: B=%d exceeds the grid limit 65535; split the batch", who, B);
+        return ASW_ERR_ARG;
+    }
+    return ASW_OK;
+}
+
+int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len, float* map_dev, void* stream) {
+    int rc = check_batch("asw_srp_score", h, mix_dev, map_dev, B);
+    if (rc != ASW_OK) return rc;
+    DeviceGuard guard(h->device);
+    if (!guard.ok) {
+        set_error("asw_srp_score: cannot make device %d current", h->device);
+        return ASW_ERR_CUDA;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int Nw = asw_srp_num_windows(T, win_len);
+    const int Nf = asw_srp_num_frames_mode(win_len, h->nfft, h->hop, h->frame_mode);
+    if (Nw < 1 || Nf < 1) {
+        // no analysis window fits: the reference leaves the map at its zero initialisation (:253)
+        ASW_CUDA_CHECK(cudaMemsetAsync(map_dev, 0, sizeof(float) * (size_t)B * h->G, s));
+        h->last_B = B;
+        h->last_Nw = 0;
+        return ASW_OK;
+    }
+    if ((rc = ensure(&h->d_gcc, &h->gcc_cap, (size_t)B * Nw * h->tab_len)) != ASW_OK) return rc;
+    if ((rc = run_gcc(h, mix_dev, B, T, win_len, Nw, Nf, h->d_gcc, s)) != ASW_OK) return rc;
+    if ((rc = run_gather(h, h->d_gcc, B, Nw, map_dev, s)) != ASW_OK) return rc;
     h->last_B = B;
     h->last_Nw = Nw;
     return ASW_OK;
+}
+
+int asw_srp_gcc(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len, float* gcc_dev, void* stream) {
+    int rc = check_batch("asw_srp_gcc", h, mix_dev, gcc_dev, B);
+    if (rc != ASW_OK) return rc;
+    DeviceGuard guard(h->device);
+    const int Nw = asw_srp_num_windows(T, win_len);
+    const int Nf = asw_srp_num_frames_mode(win_len, h->nfft, h->hop, h->frame_mode);
+    if (Nw < 1 || Nf < 1) {
+        set_error("asw_srp_gcc: no analysis window of %d samples fits T=%d", win_len, T);
+        return ASW_ERR_ARG;
+    }
+    return run_gcc(h, mix_dev, B, T, win_len, Nw, Nf, gcc_dev, (cudaStream_t)stream);
+}
+
+int asw_srp_gather(asw_srp_t* h, const float* gcc_dev, int B, int Nw, float* map_dev, void* stream) {
+    int rc = check_batch("asw_srp_gather", h, gcc_dev, map_dev, B);
+    if (rc != ASW_OK) return rc;
+    if (Nw < 1) {
+        set_error("asw_srp_gather: Nw < 1");
+        return ASW_ERR_ARG;
+    }
+    DeviceGuard guard(h->device);
+    return run_gather(h, gcc_dev, B, Nw, map_dev, (cudaStream_t)stream);
 }
 
 int asw_srp_read_cc(asw_srp_t* h, float* cc_dev, void* stream) {

@@ -24,29 +24,34 @@ def shard_range(n, rank, world):
 
 def merge_topk(vals, idxs, K):
     """Merge candidate lists (..., n) -> the K best, descending by value, ties to the lower global index
-    (the same order asw_map_topk produces).  Entries with index < 0 are padding."""
-    v = vals.clone()
+    (the same order asw_map_topk produces).  Entries with index < 0 are padding.
+    One sort of 64-bit keys (value bits, inverted index): map values are >= 0, so their float32 bit patterns
+    order like the values; -inf (padding) has a negative pattern and sorts last."""
+    v = vals.to(torch.float32).clone()
     v[idxs < 0] = float("-inf")
-    # stable two-key sort: by index ascending first, then by value descending (stable keeps index order in ties)
-    order = torch.argsort(idxs.to(torch.int64), dim=-1, stable=True)
-    v1 = torch.gather(v, -1, order)
-    i1 = torch.gather(idxs, -1, order)
-    order2 = torch.argsort(v1, dim=-1, descending=True, stable=True)
+    v = v + 0.0                                   # -0.0 -> +0.0: equal values must have equal bit patterns
+    key = (v.contiguous().view(torch.int32).to(torch.int64) << 32) | (0xFFFFFFFF - idxs.to(torch.int64).clamp(min=0))
     K = min(K, v.shape[-1])
-    order2 = order2[..., :K]
-    return torch.gather(v1, -1, order2), torch.gather(i1, -1, order2)
+    order = torch.sort(key, dim=-1, descending=True).indices[..., :K]
+    return torch.gather(v, -1, order).to(vals.dtype), torch.gather(idxs, -1, order)
 
 
 def allgather_topk(val, idx, K, group=None):
-    """All-gather every rank's (B, K) top-K lists and merge them into the global (B, K) list."""
+    """All-gather every rank's (B, K) top-K lists (one collective: values and indices packed side by side) and
+    merge them into the global (B, K) list."""
     world = dist.get_world_size(group)
     if world == 1:
         return val, idx
-    vs = [torch.empty_like(val) for _ in range(world)]
-    ix = [torch.empty_like(idx) for _ in range(world)]
-    dist.all_gather(vs, val.contiguous(), group=group)
-    dist.all_gather(ix, idx.contiguous(), group=group)
-    return merge_topk(torch.cat(vs, dim=-1), torch.cat(ix, dim=-1), K)
+    B, k = val.shape
+    pack = torch.empty((B, 2 * k), device=val.device, dtype=torch.float32)
+    pack[:, :k] = val
+    pack[:, k:] = idx.to(torch.int32).view(torch.float32)
+    flat = torch.empty((world * B, 2 * k), device=val.device, dtype=torch.float32)   # concatenated along dim 0
+    dist.all_gather_into_tensor(flat, pack, group=group)
+    gathered = flat.view(world, B, 2 * k)
+    vs = gathered[:, :, :k].permute(1, 0, 2).reshape(B, world * k)
+    ix = gathered[:, :, k:].contiguous().view(torch.int32).permute(1, 0, 2).reshape(B, world * k)
+    return merge_topk(vs, ix, K)
 
 
 def allgather_map(map_slice, G, group=None):
@@ -112,3 +117,76 @@ def native_sharded_srp(lag_samples, num_mic, device, group=None, **kw):
         return h.score(mix, window_length(mix.shape[-1]))
 
     return HypercubeShardedSRP(G, score, native.map_topk, group), h
+
+
+class TableExchangeSRP:
+    """Hypercube sharding that does not recompute the transform stage on every rank.
+
+    With plain hypercube sharding every rank runs the STFT / cross-spectrum / GCC stage for ALL mixtures, which is
+    two thirds of the scoring time at 7 mics -- two GPUs are then slower than one.  Here the transform stage is
+    sharded over MIXTURES and the gather stage over HYPERCUBES, with one all-gather of the GCC lag tables in
+    between (1.2 MB per mixture at 7 mics / 3 s):
+
+        rank r:  tables[b0:b1] = gcc_local(mix[b0:b1])          (its share of the mixtures)
+        all:     tables[0:B]   = all_gather(tables[b0:b1])      (NCCL over NVLink)
+        rank r:  map[:, g0:g1] = gather_slice(tables[0:B])      (its share of the hypercubes)
+
+    ``gcc_local`` / ``gather_slice`` are injected (native.NativeSRP.gcc / .gather on a GPU) so that the exchange
+    logic is testable with gloo on CPU.  Every rank's handle must use the same table layout: see
+    ``native_table_exchange_srp``."""
+
+    def __init__(self, gcc_local, gather_slice, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.gcc_local = gcc_local
+        self.gather_slice = gather_slice
+
+    def score_slice(self, mix):
+        """mix (B, M, T), the same on every rank -> this rank's (B, g1 - g0) slice of the map."""
+        B = mix.shape[0]
+        b0, b1 = shard_range(B, self.rank, self.world)
+        local = self.gcc_local(mix[b0:b1].contiguous())
+        if self.world == 1:
+            return self.gather_slice(local)
+        per = -(-B // self.world)
+        buf = local
+        if B % self.world:                      # ragged split: every rank contributes `per` rows, the last ones padding
+            buf = local.new_zeros((per, local.shape[1]))
+            buf[:b1 - b0] = local
+        gathered = local.new_empty((self.world * per, local.shape[1]))
+        dist.all_gather_into_tensor(gathered, buf, group=self.group)
+        if B % self.world:                      # drop every rank's padding rows
+            rows = [r * per + i for r in range(self.world)
+                    for i in range(shard_range(B, r, self.world)[1] - shard_range(B, r, self.world)[0])]
+            gathered = gathered[torch.as_tensor(rows, device=gathered.device)]
+        return self.gather_slice(gathered)
+
+
+def native_table_exchange_srp(lag_samples, num_mic, device, group=None, **kw):
+    """HypercubeShardedSRP whose slices come from a TableExchangeSRP over libasw.so.  Every rank's handle is built
+    from its lag rows [g0, g1) plus two extra rows holding the per-pair minimum and maximum lag of ALL hypercubes, so
+    that the lag-table layout (first lag, length) is the one a single-GPU handle would use: tables are then
+    exchangeable between ranks and every map value is bit-identical to the single-GPU one."""
+    import numpy as np
+    from . import native
+    from .constants import window_length
+    lag = np.ascontiguousarray(lag_samples, dtype=np.float64)
+    G = lag.shape[0]
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    g0, g1 = shard_range(G, rank, world)
+    rows = np.concatenate([lag[g0:g1], lag.min(0, keepdims=True), lag.max(0, keepdims=True)])
+    h = native.NativeSRP(rows, num_mic, device=device, **kw)
+    state = {}
+
+    def gcc_local(mix):
+        state["T"] = mix.shape[-1]
+        return h.gcc(mix, window_length(mix.shape[-1]))
+
+    def gather_slice(tables):
+        T = state["T"]
+        return h.gather(tables, h.num_windows(T, window_length(T)))[:, :g1 - g0].contiguous()
+
+    ex = TableExchangeSRP(gcc_local, gather_slice, group)
+    return HypercubeShardedSRP(G, ex.score_slice, native.map_topk, group), h

@@ -112,6 +112,37 @@ class NativeSRP:
         self._last = (B, self.num_windows(T, win_len))
         return out
 
+    def table_len(self):
+        return self.gcc_layout()[3]
+
+    def gcc(self, mix, win_len, out=None):
+        """Transform stage only (asw_srp_gcc): mix (B, M, T) float32 CUDA -> GCC lag tables (B, Nw * table_len)."""
+        _require_cuda(mix, "mix", torch.float32)
+        B, M, T = mix.shape
+        if M != self.M:
+            raise _lib.AswError(f"mix has {M} channels, handle was built for {self.M}")
+        Nw = self.num_windows(T, win_len)
+        if out is None:
+            out = torch.empty((B, Nw * self.table_len()), device=mix.device, dtype=torch.float32)
+        else:
+            _require_cuda(out, "out", torch.float32)
+        if B:
+            _lib.check(self.lib.asw_srp_gcc(self._h, _ptr(mix), B, T, int(win_len), _ptr(out), _stream(mix.device)))
+        return out
+
+    def gather(self, gcc, Nw, out=None):
+        """Gather stage only (asw_srp_gather): tables (B, Nw * table_len) -> map (B, G) of this handle's hypercubes."""
+        _require_cuda(gcc, "gcc", torch.float32)
+        B = gcc.shape[0]
+        if gcc.shape[1] != Nw * self.table_len():
+            raise _lib.AswError("gcc must be (B, Nw * table_len)")
+        if out is None:
+            out = torch.empty((B, self.G), device=gcc.device, dtype=torch.float32)
+        else:
+            _require_cuda(out, "out", torch.float32)
+        _lib.check(self.lib.asw_srp_gather(self._h, _ptr(gcc), B, int(Nw), _ptr(out), _stream(gcc.device)))
+        return out
+
     def read_cc(self):
         """CC_flat of the last score call: (B, Nw, F, P) complex64."""
         B, Nw = self._last

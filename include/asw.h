@@ -102,6 +102,15 @@ int asw_srp_num_frames_mode(int win_len, int nfft, int hop, int frame_mode);
 int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len,
                   float* map_dev, void* stream);
 
+/* The two halves of asw_srp_score, for sharding the hypercubes of one geometry over several GPUs without recomputing
+ * the transform stage on every rank: each rank runs asw_srp_gcc on ITS mixtures, the ranks all-gather the GCC lag
+ * tables (NCCL), and each rank runs asw_srp_gather on ITS hypercubes for all mixtures.  All ranks' handles must be
+ * built with the same per-pair lag range (dist.py appends the two rows of global per-pair minima / maxima to every
+ * rank's lag slice), so that the table layout -- asw_srp_gcc_layout -- is the same everywhere.
+ *   gcc_dev [B][Nw * table_len] float32, pair-major (pair p at Nw * off[p], then [Nw][npad[p]]) */
+int asw_srp_gcc(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len, float* gcc_dev, void* stream);
+int asw_srp_gather(asw_srp_t* h, const float* gcc_dev, int B, int Nw, float* map_dev, void* stream);
+
 /* Number of analysis windows / STFT frames the call above uses (host-side helper;
  * mirrors SRP_Prunning.py:393-403 and the pyroomacoustics frame rule). */
 int asw_srp_num_windows(int T, int win_len);

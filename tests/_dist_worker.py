@@ -37,6 +37,16 @@ def main():
     gmap = sharded.full_map(mix)
     val, idx = sharded.topk(mix, K)
     ok = torch.equal(gmap, full) and torch.equal(val, fval) and torch.equal(idx, fidx)
+    # table exchange: transform stage sharded over mixtures, gather over hypercubes, GCC tables all-gathered (NCCL)
+    ex, ex_handle = adist.native_table_exchange_srp(lag, scene.mic_positions.shape[0], dev)
+    emap = ex.full_map(mix)
+    eval_, eidx = ex.topk(mix, K)
+    ok = ok and torch.equal(emap, full) and torch.equal(eval_, fval) and torch.equal(eidx, fidx)
+    odd = mix[:3].contiguous()                                   # 3 mixtures over 2 ranks: ragged split
+    ok = ok and torch.equal(ex.full_map(odd), full[:3])
+    # the two halves on one handle are asw_srp_score
+    tabs = node.native.gcc(mix, window_length(72000))
+    ok = ok and torch.equal(node.native.gather(tabs, node.native.num_windows(72000, window_length(72000))), full)
     # mixture-sharded: each rank scores its slice of the batch, no communication
     b0, b1 = adist.shard_range(mix.shape[0], rank, world)
     part = node.native.score(mix[b0:b1].contiguous(), window_length(72000)) if b1 > b0 else full[:0]
