@@ -62,7 +62,7 @@ def load():
                                       i32, vp, vp, vp, vp, i32, i32, i32]
     lib.asw_select_destroy.argtypes = [vp]
     lib.asw_select_patches.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp, vp, vp, i32, vp]
-    lib.asw_subdivide.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.asw_subdivide.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
     lib.asw_select_set_grid1.argtypes = [vp, vp, vp, vp]
     lib.asw_build_shift_table.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp]
     lib.asw_shift_stack_counted.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]

@@ -407,6 +407,9 @@ struct SubParams {
     int32_t* leaf_npts;             // [n][max_leaves]
     double* leaf_box;               // [n][max_leaves][2][D]
     double* leaf_centre;            // [n][max_leaves][3] mean position of the leaf's member voxels (optional)
+    int32_t* root_members;          // [n][member_cap] 1 cm voxel indices inside the coarse patch, unordered (optional)
+    int32_t* root_count;            // [n] how many there are (may exceed member_cap: then the list is truncated)
+    int member_cap;
     const double* grid1;            // xx1 [Nx1], yy1 [Ny1], zz [Nz]
     int32_t* root_after;            // [n][2][D] root offsets / widths after check_out (the reference mutates the candidate)
     int32_t* status;                // [n] 0 ok, 1 member list overflow, 2 node overflow, 3 leaf overflow
@@ -475,6 +478,12 @@ __global__ void __launch_bounds__(kSubThreads) subdivide_kernel(SubParams q) {
     if (n_root > kListCap) {
         n_root = kListCap;
         status = 1;
+    }
+
+    if (q.root_members) {             // Patch.area_points of the candidate, as voxel indices (the host sorts them)
+        int32_t* dstm = q.root_members + (size_t)cand * q.member_cap;
+        for (int k = tid; k < n_root && k < q.member_cap; k += kSubThreads) dstm[k] = area[k];
+        if (tid == 0) q.root_count[cand] = s_n;
     }
 
     // ---- level-synchronous walk of the split tree
@@ -947,7 +956,12 @@ int asw_select_set_grid1(asw_select_t* h, const double* xx1, const double* yy1, 
 int asw_subdivide(asw_select_t* h, const int32_t* centres_dev, const int32_t* widths_dev, int n,
                   const double* upper_bound, int max_leaves, int32_t* leaf_count_dev, int32_t* leaf_off_dev,
                   int32_t* leaf_w_dev, int32_t* leaf_npts_dev, double* leaf_box_dev, double* leaf_centre_dev,
-                  int32_t* root_after_dev, int32_t* status_dev, void* stream) {
+                  int32_t* root_after_dev, int32_t* status_dev, int32_t* root_members_dev, int member_cap,
+                  int32_t* root_count_dev, void* stream) {
+    if (root_members_dev && (!root_count_dev || member_cap < 1)) {
+        set_error("asw_subdivide: root_members_dev needs root_count_dev and member_cap >= 1");
+        return ASW_ERR_ARG;
+    }
     if (leaf_centre_dev && (!h || !h->d_grid1)) {
         set_error("asw_subdivide: leaf centres need the 1 cm grid coordinates (asw_select_set_grid1)");
         return ASW_ERR_ARG;
@@ -989,6 +1003,9 @@ int asw_subdivide(asw_select_t* h, const int32_t* centres_dev, const int32_t* wi
     q.leaf_npts = leaf_npts_dev;
     q.leaf_box = leaf_box_dev;
     q.leaf_centre = leaf_centre_dev;
+    q.root_members = root_members_dev;
+    q.root_count = root_count_dev;
+    q.member_cap = member_cap;
     q.grid1 = h->d_grid1;
     q.root_after = root_after_dev;
     q.status = status_dev;

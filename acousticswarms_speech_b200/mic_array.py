@@ -110,10 +110,16 @@ class Mic_Array(object):
         for c in candidates:
             if not np.all(np.asarray(c.width_list) == c.width_list[0]):
                 raise native._lib.AswError("coarse patches must have one width in every dimension")
-        cn, off, wid, npts, box, root, centre = native.subdivide(node.native_select, torch.from_numpy(centres).to(dev),
-                                                         torch.from_numpy(widths).to(dev), self.upper_bound_pairwise)
+        cn, off, wid, npts, box, root, centre, members = native.subdivide(
+            node.native_select, torch.from_numpy(centres).to(dev), torch.from_numpy(widths).to(dev),
+            self.upper_bound_pairwise, member_cap=1 << 17)
+        pos1 = node.Pos_1.reshape(-1, 3)
         out = []
         for i, cand in enumerate(candidates):
+            if cand._area_points is None and len(members[i]) > 0:
+                # the kernel already enumerated the candidate's 1 cm voxels; ascending voxel index is the order of
+                # hyperbola_area_init's np.nonzero, so this is the same (3, n) array without the host scan
+                cand._area_fn = (lambda m=members[i]: pos1[m].T)
             root_box_lo = centres[i].astype(np.float64) - (float(widths[i]) + 0.2) / 2
             untouched = cn[i] == 1 and np.array_equal(box[i, 0, 0], root_box_lo)    # the root itself is the leaf
             parent = cand.area_points_getter()         # bound before check_out mutates the candidate; built on demand

@@ -296,11 +296,12 @@ class NativeSelect:
         return n, off, wid, pk
 
 
-def subdivide(select_handle, centres, widths, upper_bound, max_leaves=128):
+def subdivide(select_handle, centres, widths, upper_bound, max_leaves=128, member_cap=0):
     """Device search_area for n coarse patches.  centres (n, D) int32 CUDA, widths (n,) int32 CUDA,
     upper_bound (D,) float64 host.  Returns host numpy arrays
     (leaf_count (n,), leaf_off (n, L, D), leaf_w (n, L, D), leaf_npts (n, L), leaf_box (n, L, 2, D),
-    root_after (n, 2, D), leaf_centre (n, L, 3))."""
+    root_after (n, 2, D), leaf_centre (n, L, 3)) and, with ``member_cap > 0``, a list of n int64 arrays: every
+    candidate's member voxels (flat indices into the 1 cm volume) sorted ascending = the order of its area_points."""
     _require_cuda(centres, "centres", torch.int32)
     _require_cuda(widths, "widths", torch.int32)
     n, D = centres.shape
@@ -316,16 +317,30 @@ def subdivide(select_handle, centres, widths, upper_bound, max_leaves=128):
     centre = torch.zeros((n, max_leaves, 3), device=dev, dtype=torch.float64)
     root = torch.zeros((n, 2, D), device=dev, dtype=torch.int32)
     status = torch.zeros((n,), device=dev, dtype=torch.int32)
+    members = rcount = None
+    if member_cap > 0:
+        members = torch.full((n, int(member_cap)), 2 ** 31 - 1, device=dev, dtype=torch.int32)
+        rcount = torch.zeros((n,), device=dev, dtype=torch.int32)
     if n:
         _lib.check(select_handle.lib.asw_subdivide(select_handle._h, _ptr(centres), _ptr(widths), n, ub.ctypes.data,
                                                    int(max_leaves), _ptr(cnt), _ptr(off), _ptr(wid), _ptr(npts),
-                                                   _ptr(box), _ptr(centre), _ptr(root), _ptr(status), _stream(dev)))
+                                                   _ptr(box), _ptr(centre), _ptr(root), _ptr(status),
+                                                   _ptr(members) if members is not None else None, int(member_cap),
+                                                   _ptr(rcount) if rcount is not None else None, _stream(dev)))
     st = status.cpu().numpy()
     cn = cnt.cpu().numpy()
     if (st != 0).any() or (cn > max_leaves).any():
         raise _lib.AswError(f"asw_subdivide: capacity exceeded (status {st.tolist()}, leaves {cn.tolist()})")
-    return (cn, off.cpu().numpy(), wid.cpu().numpy(), npts.cpu().numpy(), box.cpu().numpy(), root.cpu().numpy(),
-            centre.cpu().numpy())
+    out = (cn, off.cpu().numpy(), wid.cpu().numpy(), npts.cpu().numpy(), box.cpu().numpy(), root.cpu().numpy(),
+           centre.cpu().numpy())
+    if members is None:
+        return out
+    rc = rcount.cpu().numpy()
+    if (rc > member_cap).any():
+        raise _lib.AswError(f"asw_subdivide: member list capacity {member_cap} exceeded ({int(rc.max())} voxels)")
+    width = int(rc.max(initial=0))
+    srt = torch.sort(members[:, :max(width, 1)], dim=1).values.cpu().numpy() if n else np.zeros((0, 1), dtype=np.int32)
+    return out + ([srt[i, :rc[i]].astype(np.int64) for i in range(n)],)
 
 
 def build_shift_table(n_patches, offsets, capacity, shifts=None, mix_index=None, n_total=None):

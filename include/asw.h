@@ -241,12 +241,17 @@ int asw_select_patches(asw_select_t* h, const float* map_dev, const int32_t* pea
  *                                            candidate's area_points (so the host can rebuild them in order)
  *   leaf_centre [n][max_leaves][3] float64   Patch.center_pos() of the leaf = mean position of its member voxels
  *                                            (NaN for an empty leaf); may be NULL
+ *   root_members [n][member_cap] int32       the candidate's own area_points (hyperbola_area_init, SRP_Prunning.py:41-61)
+ *                                            as flat indices (iy * Nx1 + ix) * Nz + iz into the 1 cm volume, UNORDERED;
+ *                                            sorted ascending they are the reference's order.  root_count [n] is their
+ *                                            number (a count above member_cap means the list was truncated).  May be NULL.
  *   root_after [n][2][D] int32   the candidate's offsets / widths after check_out (the reference mutates it in place)
  *   status [n] int32             0 ok; 1/2/3 = member-list / node / leaf capacity exceeded (results incomplete) */
 int asw_subdivide(asw_select_t* h, const int32_t* centres_dev, const int32_t* widths_dev, int n,
                   const double* upper_bound, int max_leaves, int32_t* leaf_count_dev, int32_t* leaf_off_dev,
                   int32_t* leaf_w_dev, int32_t* leaf_npts_dev, double* leaf_box_dev, double* leaf_centre_dev,
-                  int32_t* root_after_dev, int32_t* status_dev, void* stream);
+                  int32_t* root_after_dev, int32_t* status_dev, int32_t* root_members_dev, int member_cap,
+                  int32_t* root_count_dev, void* stream);
 /* Coordinates of the 1 cm volume (np.arange of SRP_Prunning.py:158-160: xx1 [Nx1], yy1 [Ny1], zz [Nz], host
  * arrays); needed once per handle before asw_subdivide is asked for leaf centres. */
 int asw_select_set_grid1(asw_select_t* h, const double* xx1, const double* yy1, const double* zz);

@@ -458,6 +458,10 @@ def test_device_subdivision_equals_host(cuda_device, desk):
                     c.area_points                     # materialise before deepcopy-independent use
                 dev_c = copy.deepcopy(host_c)
                 want = [local_utils.search_area([c], scene.mic_positions, ub) for c in host_c]
+                lazy_c = copy.deepcopy(cands)              # area_points not built yet: the device supplies the members
+                ma._search_area_device(lazy_c)
+                for lc, hc in zip(lazy_c, host_c):
+                    assert np.array_equal(lc.area_points, hc.area_points)
                 got = ma._search_area_device(dev_c)
                 for w, gl, hc, dc in zip(want, got, host_c, dev_c):
                     # center_pos() of a leaf: the device mean of its member voxels, available without building
