@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <atomic>
 #include <stdio.h>
 
 #include "../../include/asw.h"
@@ -56,14 +58,12 @@ struct DeviceGuard {
 
 // cudaFuncSetAttribute is per device: true the first time a kernel is configured on the current device.
 struct PerDeviceOnce {
-    unsigned long long mask = 0;
+    std::atomic<unsigned long long> mask{0};
     bool need() {
         int d = 0;
         cudaGetDevice(&d);
         const unsigned long long bit = 1ull << (d & 63);
-        const bool first = !(mask & bit);
-        mask |= bit;
-        return first;
+        return !(mask.fetch_or(bit) & bit);
     }
 };
 
