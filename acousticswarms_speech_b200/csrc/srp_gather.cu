@@ -131,14 +131,18 @@ int launch_t(SrpGatherParams p, int tile, cudaStream_t s) {
     return ASW_OK;
 }
 
-// Hypercubes per CTA.  Every CTA stages the mixture's whole GCC table; the copy is asynchronous, but its shared-memory
-// writes compete with the gathers (~s_eq hypercubes' worth of wavefronts), and one CTA fits per SM, so the kernel runs
-// in ceil(CTAs / 148) rounds of (s_eq + tile): pick the tile that minimises it -- e.g. G = 21181, B = 32:
-// 2048 -> 352 CTAs = 2.4 rounds, 1632 -> 416 CTAs = 2.8 rounds.
+// Hypercubes per CTA.  Every CTA stages the mixture's whole GCC table group by group (copies are asynchronous, but
+// the per-group barriers and the shared-memory writes are a fixed cost per CTA, ~s_eq hypercubes' worth of gathers),
+// and one CTA fits per SM, so the kernel runs in ceil(CTAs / 148) rounds of (s_eq + tile): pick the tile that
+// minimises it.  Calibration (C2, B = 32, G = 21181): tile 1184 -> 576 CTAs, 4 rounds of 45 us; tile 1632 -> 416 CTAs,
+// 3 rounds of 50 us  =>  fixed cost ~32 us = ~2850 hypercubes; tiles above 2048 use the 3-per-thread variant.
+constexpr int kThreads3 = 800;                  // 3 hypercubes per thread need ~80 registers: 25 warps per CTA
+constexpr int kMaxTile = 3 * kThreads3;
+
 int choose_tile(int G, int B, int P, int tab_len) {
-    const int kMinTile = 512, kMaxTile = 2 * kMaxThreads;
-    const double s_eq = 0.12 * (double)tab_len / (double)(P > 0 ? P : 1);
-    int best_tile = kMaxTile;
+    const int kMinTile = 512;
+    const double s_eq = 2.0 * (double)tab_len / (double)(P > 0 ? P : 1);
+    int best_tile = 2 * kMaxThreads;
     double best_cost = 1e300;
     for (int nt = (G + kMaxTile - 1) / kMaxTile; nt <= (G + kMinTile - 1) / kMinTile; ++nt) {
         int tile = ((G + nt - 1) / nt + 31) / 32 * 32;
@@ -166,6 +170,7 @@ int launch_srp_gather(const SrpGatherParams& p, cudaStream_t s) {
         return ASW_ERR_RANGE;
     }
     const int tile = choose_tile(p.G, p.B, p.P, p.tab_len);
+    if (tile > 2 * kMaxThreads) return launch_t<3, kThreads3>(p, tile, s);
     if (tile > kMaxThreads) return launch_t<2, kMaxThreads>(p, tile, s);
     return launch_t<1, kMaxThreads>(p, tile, s);
 }
