@@ -1,5 +1,6 @@
 // api.cu -- C ABI of libasw.so (declared in include/asw.h): handle management, host-side table
 // construction and the launch sequence of the scoring path.
+#include <limits.h>
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
@@ -43,9 +44,13 @@ struct asw_srp {
     float2* d_twpost = nullptr;  // [F]
     float* d_fir = nullptr;      // [(U-1)][12] upsampling weights of gcc.cu
     // staging groups of the gather kernel, one set per window-chunk size
-    std::vector<int> grp_begin;
-    int* d_grp_begin = nullptr;
-    int n_groups = 0, grp_wc = 0, smem_bytes = 0;
+    // staging plans of the gather kernel, one per (hypercubes per CTA, windows per chunk) combination seen so far
+    struct GatherPlan {
+        int tile = 0, wc = 0, stage_floats = 0;
+        int *d_rng_lo = nullptr, *d_rng_n = nullptr, *d_tile_grp = nullptr, *d_grp_flat = nullptr;
+    };
+    std::vector<GatherPlan> plans;
+    std::vector<uint32_t> pos_host;   // [P][Gpad] copy of d_pos (plans are built from it)
     // workspace (grown on demand)
     float2* d_cc_part = nullptr;
     size_t cc_part_cap = 0;
@@ -91,35 +96,77 @@ void kd_order(const double* lag, int P, int* idx, int n) {
     kd_order(lag, P, idx + mid, n - mid);
 }
 
-int build_groups(asw_srp* h, int wc) {
+// Staging plan for CTAs of `tile` hypercubes (slot order) and `wc` windows per chunk: for every tile and pair the
+// range of table entries the tile's 4-tap gathers touch (a k-d tile covers about a quarter of a pair's lags), and the
+// partition of the pairs into groups that fit one shared-memory stage.
+int build_plan(asw_srp* h, int tile, int wc, const asw_srp::GatherPlan** out) {
+    for (const auto& pl : h->plans)
+        if (pl.tile == tile && pl.wc == wc) {
+            *out = &pl;
+            return ASW_OK;
+        }
     const int budget = srp_gather_smem_budget();
-    h->grp_begin.clear();
-    h->grp_begin.push_back(0);
-    int cur = 0, max_bytes = 0;
-    for (int p = 0; p < h->P; ++p) {
-        const int bytes = wc * h->npad[p] * (int)sizeof(float);
-        if (bytes > budget) {
-            set_error("lag table of pair %d (%d entries x %d windows) exceeds the shared-memory stage of %d bytes; "
-                      "lower the oversampling",
-                      p, h->npad[p], wc, budget);
-            return ASW_ERR_RANGE;
+    const int P = h->P, G = h->G, ntiles = (G + tile - 1) / tile;
+    std::vector<int> lo((size_t)ntiles * P), nn((size_t)ntiles * P), tile_grp(ntiles + 1), flat;
+    int max_bytes = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        const int s0 = t * tile, s1 = std::min(G, s0 + tile);
+        tile_grp[t] = (int)flat.size();
+        flat.push_back(0);
+        int cur = 0;
+        for (int p = 0; p < P; ++p) {
+            const uint32_t* row = h->pos_host.data() + (size_t)p * h->Gpad;
+            int mn = INT_MAX, mx = INT_MIN;
+            for (int sl = s0; sl < s1; ++sl) {
+                const int i0 = (int)(row[sl] >> kFracBits);
+                mn = std::min(mn, i0);
+                mx = std::max(mx, i0);
+            }
+            const int l = (mn - 1) & ~3;                         // taps i0 - 1 .. i0 + 2
+            const int n = ((mx + 2 - l + 1) + 3) & ~3;
+            lo[(size_t)t * P + p] = l;
+            nn[(size_t)t * P + p] = n;
+            const int bytes = wc * n * (int)sizeof(float);
+            if (l < 0 || l + n > h->npad[p] || bytes > budget) {
+                set_error("gather plan: pair %d needs %d entries x %d windows per stage (limit %d bytes); lower the "
+                          "oversampling", p, n, wc, budget);
+                return ASW_ERR_RANGE;
+            }
+            if (cur + bytes > budget) {
+                flat.push_back(p);
+                cur = 0;
+            }
+            cur += bytes;
+            max_bytes = std::max(max_bytes, cur);
         }
-        if (cur + bytes > budget) {
-            h->grp_begin.push_back(p);
-            cur = 0;
-        }
-        cur += bytes;
-        if (cur > max_bytes) max_bytes = cur;
+        flat.push_back(P);
     }
-    h->grp_begin.push_back(h->P);
-    h->n_groups = (int)h->grp_begin.size() - 1;
-    h->grp_wc = wc;
-    h->smem_bytes = max_bytes;
-    if (h->d_grp_begin) cudaFree(h->d_grp_begin);
-    h->d_grp_begin = nullptr;
-    ASW_CUDA_CHECK(cudaMalloc(&h->d_grp_begin, sizeof(int) * h->grp_begin.size()));
-    ASW_CUDA_CHECK(cudaMemcpy(h->d_grp_begin, h->grp_begin.data(), sizeof(int) * h->grp_begin.size(),
-                              cudaMemcpyHostToDevice));
+    tile_grp[ntiles] = (int)flat.size();
+    asw_srp::GatherPlan pl;
+    pl.tile = tile;
+    pl.wc = wc;
+    pl.stage_floats = max_bytes / (int)sizeof(float);
+    auto up = [](int** d, const std::vector<int>& v) {
+        cudaError_t e = cudaMalloc(d, sizeof(int) * v.size());
+        if (e == cudaSuccess) e = cudaMemcpy(*d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice);
+        return e;
+    };
+    cudaError_t e = up(&pl.d_rng_lo, lo);
+    if (e == cudaSuccess) e = up(&pl.d_rng_n, nn);
+    if (e == cudaSuccess) e = up(&pl.d_tile_grp, tile_grp);
+    if (e == cudaSuccess) e = up(&pl.d_grp_flat, flat);
+    if (e != cudaSuccess) {
+        set_error("gather plan: %s", cudaGetErrorString(e));
+        cudaFree(pl.d_rng_lo); cudaFree(pl.d_rng_n); cudaFree(pl.d_tile_grp); cudaFree(pl.d_grp_flat);
+        return ASW_ERR_CUDA;
+    }
+    h->plans.reserve(16);                                        // pointers into the vector stay valid
+    if (h->plans.size() >= 16) {                                 // a caller cycling through many batch shapes: start over
+        for (auto& q : h->plans) { cudaFree(q.d_rng_lo); cudaFree(q.d_rng_n); cudaFree(q.d_tile_grp); cudaFree(q.d_grp_flat); }
+        h->plans.clear();
+    }
+    h->plans.push_back(pl);
+    *out = &h->plans.back();
     return ASW_OK;
 }
 
@@ -334,6 +381,7 @@ int asw_srp_create(asw_srp_t** out, int device, int M, int G, const double* lag,
         TRY(cudaMemcpy(h->d_npad, h->npad.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
         TRY(cudaMemcpy(h->d_off, h->off.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
         TRY(cudaMemcpy(h->d_pos, pos.data(), sizeof(uint32_t) * pos.size(), cudaMemcpyHostToDevice));
+        h->pos_host = pos;
         TRY(cudaMemcpy(h->d_tw1024, tw.data(), sizeof(float2) * kNc, cudaMemcpyHostToDevice));
         TRY(cudaMemcpy(h->d_twpost, twp.data(), sizeof(float2) * h->F, cudaMemcpyHostToDevice));
 #undef TRY
@@ -359,7 +407,7 @@ int asw_srp_destroy(asw_srp_t* h) {
     cudaFree(h->d_tw1024);
     cudaFree(h->d_twpost);
     cudaFree(h->d_fir);
-    cudaFree(h->d_grp_begin);
+    for (auto& q : h->plans) { cudaFree(q.d_rng_lo); cudaFree(q.d_rng_n); cudaFree(q.d_tile_grp); cudaFree(q.d_grp_flat); }
     cudaFree(h->d_cc_part);
     cudaFree(h->d_cc);
     cudaFree(h->d_gcc);
@@ -448,26 +496,29 @@ static int run_gcc(asw_srp* h, const float* mix_dev, int B, int T, int win_len, 
 // Stage 3: steered response of every hypercube of the handle from GCC tables `gcc` ([B][Nw * tab_len]).
 static int run_gather(asw_srp* h, const float* gcc, int B, int Nw, float* map_dev, cudaStream_t s) {
     const int wc = Nw < srp_gather_windows_per_chunk() ? Nw : srp_gather_windows_per_chunk();
-    if (h->grp_wc != wc) {
-        int rc = build_groups(h, wc);
-        if (rc != ASW_OK) return rc;
-    }
+    const int tile = srp_gather_choose_tile(h->G, B, h->P, h->tab_len);
+    const asw_srp::GatherPlan* pl = nullptr;
+    int rc = build_plan(h, tile, wc, &pl);
+    if (rc != ASW_OK) return rc;
     SrpGatherParams rp{};
     rp.gcc = gcc;
     rp.pos = h->d_pos;
+    rp.perm = h->d_perm;
     rp.npad = h->d_npad;
     rp.off = h->d_off;
-    rp.grp_begin = h->d_grp_begin;
+    rp.rng_lo = pl->d_rng_lo;
+    rp.rng_n = pl->d_rng_n;
+    rp.tile_grp = pl->d_tile_grp;
+    rp.grp_flat = pl->d_grp_flat;
     rp.map = map_dev;
     rp.B = B;
     rp.G = h->G;
     rp.Gpad = h->Gpad;
-    rp.perm = h->d_perm;
     rp.P = h->P;
     rp.Nw = Nw;
     rp.tab_len = h->tab_len;
-    rp.n_groups = h->n_groups;
-    rp.smem_bytes = h->smem_bytes;
+    rp.tile = tile;
+    rp.stage_floats = pl->stage_floats;
     return launch_srp_gather(rp, s);
 }
 

@@ -117,15 +117,21 @@ struct SrpGatherParams {
     const int* perm;        // [Gpad] slot -> hypercube index (-1 = padding)
     const int* npad;        // [P]
     const int* off;         // [P]
-    const int* grp_begin;   // [n_groups + 1] pair ranges staged together
+    // staging plan of this (tile, windows-per-chunk) combination: a CTA stages, per pair, only the table entries its
+    // hypercubes' 4-tap windows touch
+    const int* rng_lo;      // [ntiles][P] first staged entry (multiple of 4)
+    const int* rng_n;       // [ntiles][P] staged entries (multiple of 4)
+    const int* tile_grp;    // [ntiles + 1] offset of each tile's group list in grp_flat
+    const int* grp_flat;    // per tile: pair boundaries of its staging groups (n_groups + 1 entries)
     float* map;             // [B][G]
-    int B, G, Gpad, P, Nw, tab_len, n_groups, smem_bytes;
-    int tile;               // hypercubes per CTA (chosen by launch_srp_gather)
+    int B, G, Gpad, P, Nw, tab_len;
+    int tile;               // hypercubes per CTA
     int stage_floats;       // floats per stage buffer (two stages)
 };
-int launch_srp_gather(const SrpGatherParams& p, cudaStream_t s);
+int launch_srp_gather(const SrpGatherParams& p, cudaStream_t s);      // p.tile / p.stage_floats from the plan
 int srp_gather_windows_per_chunk();
 int srp_gather_smem_budget();
+int srp_gather_choose_tile(int G, int B, int P, int tab_len);
 
 int launch_topk(const float* map, int B, int G, int K, int idx_offset, float* val, int32_t* idx, cudaStream_t s);
 

@@ -25,13 +25,21 @@ constexpr int kSmemBudget = 100 * 1024;   // bytes of GCC table per stage; two s
 template <int GPT, int kThreads>
 __global__ void __launch_bounds__(kThreads, kMaxThreads / kThreads) srp_gather_kernel(SrpGatherParams p) {
     extern __shared__ __align__(16) float s_tab[];
-    const int tid = threadIdx.x;
-    const int b = blockIdx.y;
-    const int g_base = blockIdx.x * p.tile;   // p.tile <= kThreads * GPT hypercubes per CTA
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kThreads / 32;
+    const int b = blockIdx.y, t = blockIdx.x;
+    const int g_base = t * p.tile;            // p.tile <= kThreads * GPT hypercubes per CTA
     bool on[GPT];
 #pragma unroll
-    for (int gi = 0; gi < GPT; ++gi) on[gi] = gi * kThreads + tid < p.tile;
+    for (int gi = 0; gi < GPT; ++gi) {
+        const int sl = gi * kThreads + tid;
+        on[gi] = sl < p.tile && g_base + sl < p.G;
+    }
     const float* gcc_b = p.gcc + (size_t)b * p.tab_len * p.Nw;
+    const int* rlo = p.rng_lo + (size_t)t * p.P;
+    const int* rn = p.rng_n + (size_t)t * p.P;
+    const int* gb = p.grp_flat + p.tile_grp[t];
+    const int n_groups = p.tile_grp[t + 1] - p.tile_grp[t] - 1;
 
     float best[GPT];
 #pragma unroll
@@ -45,39 +53,42 @@ __global__ void __launch_bounds__(kThreads, kMaxThreads / kThreads) srp_gather_k
 #pragma unroll
             for (int gi = 0; gi < GPT; ++gi) acc[w][gi] = 0.f;
 
-        // asynchronous copy of one group of pair tables (this chunk's windows) into a stage buffer
+        // asynchronous copy of one group of pair tables into a stage buffer: for every pair the rows of this chunk's
+        // windows, restricted to the entries [lo, lo + n) this tile touches; one (pair, window) row per warp
         auto stage = [&](int grp, float* buf) {
-            const int q0 = p.grp_begin[grp], q1 = p.grp_begin[grp + 1];
-            int so = 0;
+            const int q0 = gb[grp], q1 = gb[grp + 1];
+            int so = 0, row = 0;
             for (int pp = q0; pp < q1; ++pp) {
-                const int npd = p.npad[pp];
-                const float* src = gcc_b + (size_t)p.Nw * p.off[pp] + (size_t)w0 * npd;
-                const int n4 = (wc * npd) >> 2;
-                for (int i = tid; i < n4; i += kThreads) {
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
-                                     (unsigned)__cvta_generic_to_shared(buf + so + 4 * i)),
-                                 "l"(src + 4 * i));
+                const int npd = p.npad[pp], n = rn[pp], lo = rlo[pp];
+                const float* src = gcc_b + (size_t)p.Nw * p.off[pp] + (size_t)w0 * npd + lo;
+                for (int w = 0; w < wc; ++w, ++row) {
+                    if (row % kWarps != warp) continue;
+                    const float* sr = src + (size_t)w * npd;
+                    float* ds = buf + so + w * n;
+                    for (int k = 4 * lane; k < n; k += 128)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                                         (unsigned)__cvta_generic_to_shared(ds + k)),
+                                     "l"(sr + k));
                 }
-                so += wc * npd;
+                so += wc * n;
             }
             asm volatile("cp.async.commit_group;\n" ::);
         };
         __syncthreads();  // the previous chunk's last stage is no longer read
         stage(0, s_tab);
-        for (int grp = 0; grp < p.n_groups; ++grp) {
-            const int p0 = p.grp_begin[grp], p1 = p.grp_begin[grp + 1];
+        for (int grp = 0; grp < n_groups; ++grp) {
+            const int p0 = gb[grp], p1 = gb[grp + 1];
             const float* s_cur = s_tab + (grp & 1) * p.stage_floats;
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");   // this thread's part of group `grp` has landed
             __syncthreads();  // everybody's part has, and everybody is done gathering from the other stage
-            if (grp + 1 < p.n_groups) stage(grp + 1, s_tab + ((grp + 1) & 1) * p.stage_floats);
+            if (grp + 1 < n_groups) stage(grp + 1, s_tab + ((grp + 1) & 1) * p.stage_floats);
             int sm_off = 0;
             for (int pp = p0; pp < p1; ++pp) {
-                const int npd = p.npad[pp];
+                const int n = rn[pp], lo = rlo[pp];
 #pragma unroll
                 for (int gi = 0; gi < GPT; ++gi) {
                     if (!on[gi]) continue;
-                    const uint32_t q =
-                        __ldg(p.pos + (size_t)pp * p.Gpad + min(g_base + gi * kThreads + tid, p.Gpad - 1));
+                    const uint32_t q = __ldg(p.pos + (size_t)pp * p.Gpad + g_base + gi * kThreads + tid);
                     const int i0 = (int)(q >> kFracBits);
                     const float f = (float)(q & ((1u << kFracBits) - 1)) * (1.0f / (float)(1 << kFracBits));
                     // 4-tap Lagrange weights for nodes -1, 0, 1, 2
@@ -86,20 +97,20 @@ __global__ void __launch_bounds__(kThreads, kMaxThreads / kThreads) srp_gather_k
                     const float c1 = 0.5f * fp1 * fm1 * fm2;
                     const float c2 = -0.5f * fp1 * f * fm2;
                     const float c3 = (1.f / 6.f) * fp1 * f * fm1;
-                    const float* t = s_cur + sm_off + i0 - 1;
+                    const float* tp = s_cur + sm_off + (i0 - lo) - 1;
 #pragma unroll
                     for (int w = 0; w < kWc; ++w) {
                         if (w < wc) {
-                            float v = c0 * t[0];
-                            v = fmaf(c1, t[1], v);
-                            v = fmaf(c2, t[2], v);
-                            v = fmaf(c3, t[3], v);
+                            float v = c0 * tp[0];
+                            v = fmaf(c1, tp[1], v);
+                            v = fmaf(c2, tp[2], v);
+                            v = fmaf(c3, tp[3], v);
                             acc[w][gi] += v;
-                            t += npd;
+                            tp += n;
                         }
                     }
                 }
-                sm_off += wc * npd;
+                sm_off += wc * n;
             }
         }
 #pragma unroll
@@ -112,21 +123,19 @@ __global__ void __launch_bounds__(kThreads, kMaxThreads / kThreads) srp_gather_k
 #pragma unroll
     for (int gi = 0; gi < GPT; ++gi) {
         const int slot = g_base + gi * kThreads + tid;
-        if (on[gi] && slot < p.G) p.map[(size_t)b * p.G + p.perm[slot]] = best[gi];
+        if (on[gi]) p.map[(size_t)b * p.G + p.perm[slot]] = best[gi];
     }
 }
 
 template <int GPT, int kThreads>
-int launch_t(SrpGatherParams p, int tile, cudaStream_t s) {
+int launch_t(const SrpGatherParams& p, cudaStream_t s) {
     static PerDeviceOnce attr_once;
     if (attr_once.need()) {
         ASW_CUDA_CHECK(cudaFuncSetAttribute(srp_gather_kernel<GPT, kThreads>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kSmemBudget));
     }
-    p.tile = tile;
-    dim3 grid((p.G + tile - 1) / tile, p.B);
-    p.stage_floats = p.smem_bytes / 4;
-    srp_gather_kernel<GPT, kThreads><<<grid, kThreads, 2 * p.smem_bytes, s>>>(p);
+    dim3 grid((p.G + p.tile - 1) / p.tile, p.B);
+    srp_gather_kernel<GPT, kThreads><<<grid, kThreads, 2 * (size_t)p.stage_floats * sizeof(float), s>>>(p);
     ASW_LAUNCH_CHECK("srp_gather_kernel");
     return ASW_OK;
 }
@@ -141,7 +150,8 @@ constexpr int kMaxTile = 3 * kThreads3;
 
 int choose_tile(int G, int B, int P, int tab_len) {
     const int kMinTile = 512;
-    const double s_eq = 2.0 * (double)tab_len / (double)(P > 0 ? P : 1);
+    // a k-d tile touches roughly a quarter of every pair's table (C2: 0.20 - 0.27 for tiles of 1184 - 2368)
+    const double s_eq = 0.6 * (double)tab_len / (double)(P > 0 ? P : 1);
     int best_tile = 2 * kMaxThreads;
     double best_cost = 1e300;
     for (int nt = (G + kMaxTile - 1) / kMaxTile; nt <= (G + kMinTile - 1) / kMinTile; ++nt) {
@@ -164,15 +174,16 @@ int choose_tile(int G, int B, int P, int tab_len) {
 int srp_gather_windows_per_chunk() { return kWc; }
 int srp_gather_smem_budget() { return kSmemBudget; }
 
+int srp_gather_choose_tile(int G, int B, int P, int tab_len) { return choose_tile(G, B, P, tab_len); }
+
 int launch_srp_gather(const SrpGatherParams& p, cudaStream_t s) {
-    if (p.smem_bytes > kSmemBudget) {
-        set_error("srp_gather: stage of %d bytes exceeds the shared-memory budget", p.smem_bytes);
+    if ((size_t)p.stage_floats * sizeof(float) > (size_t)kSmemBudget) {
+        set_error("srp_gather: stage of %zu bytes exceeds the shared-memory budget", (size_t)p.stage_floats * sizeof(float));
         return ASW_ERR_RANGE;
     }
-    const int tile = choose_tile(p.G, p.B, p.P, p.tab_len);
-    if (tile > 2 * kMaxThreads) return launch_t<3, kThreads3>(p, tile, s);
-    if (tile > kMaxThreads) return launch_t<2, kMaxThreads>(p, tile, s);
-    return launch_t<1, kMaxThreads>(p, tile, s);
+    if (p.tile > 2 * kMaxThreads) return launch_t<3, kThreads3>(p, s);
+    if (p.tile > kMaxThreads) return launch_t<2, kMaxThreads>(p, s);
+    return launch_t<1, kMaxThreads>(p, s);
 }
 
 }  // namespace asw
