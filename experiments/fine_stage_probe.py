@@ -10,7 +10,7 @@ from acousticswarms_speech_b200.spot import DataParallelSpotModel
 
 class Net(torch.nn.Module):
     def forward(self, x, cond):
-        return x.mean(1, keepdim=True) * cond[:, 1:2].unsqueeze(-1) + 2 * x[:, :1] * cond[:, 0:1].unsqueeze(-1)
+        return x.mean(1, keepdim=True) * (cond[:, 1:2] + 2 * cond[:, 0:1]).unsqueeze(-1)
 
 
 class HostPowersOnly:

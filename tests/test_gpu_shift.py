@@ -94,6 +94,24 @@ def test_shift_stack_norm(cuda_device):
     assert np.abs(dn.cpu().numpy() - want).max() <= 1e-4 * np.abs(want).max()
 
 
+def test_shift_stack_norm_is_reproducible(cuda_device):
+    """The statistics pass reduces in a fixed order (no atomics across CTAs): repeated calls, alone or as part of a
+    larger batch, return the same bits."""
+    from acousticswarms_speech_b200 import native
+    rng = np.random.default_rng(12)
+    B, M, T, N = 3, 7, 144000, 40
+    mix = torch.from_numpy((0.1 * rng.standard_normal((B, M, T))).astype(np.float32)).cuda()
+    shifts = torch.from_numpy(rng.integers(-350, 351, size=(N, M)).astype(np.int32)).cuda()
+    shifts[:, 0] = 0
+    mi = torch.from_numpy(rng.integers(0, B, size=N).astype(np.int32)).cuda()
+    a = [t.clone() for t in native.shift_stack_norm(mix, shifts, mi)]
+    for _ in range(3):
+        b = native.shift_stack_norm(mix, shifts, mi)
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+    c = native.shift_stack_norm(mix, shifts[7:19].contiguous(), mi[7:19].contiguous())
+    assert torch.equal(c[0], a[0][7:19]) and torch.equal(c[1], a[1][7:19]) and torch.equal(c[2], a[2][7:19])
+
+
 def test_pcm16_ingest_is_exact(cuda_device):
     from acousticswarms_speech_b200 import native
     rng = np.random.default_rng(2)
