@@ -62,6 +62,7 @@ struct asw_srp {
     size_t gcc_cap = 0;
     // shape of the last score call (for the stage taps)
     int last_B = 0, last_Nw = 0;
+    bool gcc_internal = false;   // the last call left its GCC tables in d_gcc (asw_srp_score), not in a caller buffer
 };
 
 namespace {
@@ -557,6 +558,7 @@ int asw_srp_score(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len,
     if ((rc = run_gather(h, h->d_gcc, B, Nw, map_dev, s)) != ASW_OK) return rc;
     h->last_B = B;
     h->last_Nw = Nw;
+    h->gcc_internal = true;
     return ASW_OK;
 }
 
@@ -570,7 +572,13 @@ int asw_srp_gcc(asw_srp_t* h, const float* mix_dev, int B, int T, int win_len, f
         set_error("asw_srp_gcc: no analysis window of %d samples fits T=%d", win_len, T);
         return ASW_ERR_ARG;
     }
-    return run_gcc(h, mix_dev, B, T, win_len, Nw, Nf, gcc_dev, (cudaStream_t)stream);
+    rc = run_gcc(h, mix_dev, B, T, win_len, Nw, Nf, gcc_dev, (cudaStream_t)stream);
+    if (rc == ASW_OK) {          // asw_srp_read_cc taps this call's cross-spectra; the tables went to the caller
+        h->last_B = B;
+        h->last_Nw = Nw;
+        h->gcc_internal = false;
+    }
+    return rc;
 }
 
 int asw_srp_gather(asw_srp_t* h, const float* gcc_dev, int B, int Nw, float* map_dev, void* stream) {
@@ -614,6 +622,10 @@ int asw_srp_gcc_layout(asw_srp_t* h, int* lag_lo, int* n_entries, int* offset, i
 int asw_srp_read_gcc(asw_srp_t* h, float* gcc_dev, void* stream) {
     if (!h || !gcc_dev) {
         set_error("asw_srp_read_gcc: null argument");
+        return ASW_ERR_ARG;
+    }
+    if (!h->gcc_internal && h->last_Nw > 0) {
+        set_error("asw_srp_read_gcc: the last call (asw_srp_gcc) wrote its tables to the caller's buffer");
         return ASW_ERR_ARG;
     }
     DeviceGuard guard(h->device);
