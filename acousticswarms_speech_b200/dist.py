@@ -25,12 +25,13 @@ def shard_range(n, rank, world):
 def merge_topk(vals, idxs, K):
     """Merge candidate lists (..., n) -> the K best, descending by value, ties to the lower global index
     (the same order asw_map_topk produces).  Entries with index < 0 are padding.
-    One sort of 64-bit keys (value bits, inverted index): map values are >= 0, so their float32 bit patterns
-    order like the values; -inf (padding) has a negative pattern and sorts last."""
+    One sort of 64-bit keys (order-preserving integer image of the float32 value, inverted index)."""
     v = vals.to(torch.float32).clone()
     v[idxs < 0] = float("-inf")
     v = v + 0.0                                   # -0.0 -> +0.0: equal values must have equal bit patterns
-    key = (v.contiguous().view(torch.int32).to(torch.int64) << 32) | (0xFFFFFFFF - idxs.to(torch.int64).clamp(min=0))
+    bits = v.contiguous().view(torch.int32)
+    bits = bits ^ ((bits >> 31) & 0x7FFFFFFF)     # negative floats: flip the magnitude bits so that ints order like floats
+    key = (bits.to(torch.int64) << 32) | (0xFFFFFFFF - idxs.to(torch.int64).clamp(min=0))
     K = min(K, v.shape[-1])
     order = torch.sort(key, dim=-1, descending=True).indices[..., :K]
     return torch.gather(v, -1, order).to(vals.dtype), torch.gather(idxs, -1, order)

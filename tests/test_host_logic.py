@@ -167,6 +167,24 @@ def test_merge_topk_order_and_ties():
     assert i.tolist() == [[2, 11, 30, 7]] and v.tolist()[0][:3] == [pytest.approx(0.9)] * 3
 
 
+def test_merge_topk_matches_a_naive_merge():
+    """Random candidate lists with many ties, padding and negative values against a lexicographic sort."""
+    import torch
+    rng = np.random.default_rng(21)
+    for _ in range(20):
+        B, n, K = 3, 40, 9
+        vals = rng.choice([-1.5, -0.25, 0.0, 0.25, 0.5, 2.0], size=(B, n)).astype(np.float32)
+        idxs = np.stack([rng.permutation(200)[:n] for _ in range(B)]).astype(np.int32)
+        idxs[rng.random((B, n)) < 0.2] = -1
+        v, i = dist.merge_topk(torch.from_numpy(vals), torch.from_numpy(idxs), K)
+        for b in range(B):
+            cand = [(-float(vals[b, k]), int(idxs[b, k])) for k in range(n) if idxs[b, k] >= 0]
+            cand.sort()
+            want = cand[:K]
+            got = [(-float(a), int(c)) for a, c in zip(v[b], i[b]) if c >= 0]
+            assert got == want[:len(got)] and len(got) == min(K, len(cand))
+
+
 def test_window_constants():
     assert constants.window_length(144000) == 36000 and constants.window_length(60000) == 24000
     assert constants.frames_per_window(36000) == 67 and constants.frames_per_window(24000) == 43
