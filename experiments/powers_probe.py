@@ -1,8 +1,13 @@
 """Time asw_patch_powers against the reference's per-row numpy loop (Mic_Array.py:288-296) on a
 fine-stage sized batch: 604 rows x 144000 samples."""
+import os
+import sys
 import time
+
 import numpy as np
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from acousticswarms_speech_b200 import native
 from acousticswarms_speech_b200.local_utils import max_avg_power
 
