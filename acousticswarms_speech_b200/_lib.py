@@ -18,6 +18,7 @@ SYMBOLS = [
     "asw_select_create", "asw_select_destroy", "asw_select_patches", "asw_subdivide",
     "asw_build_shift_table", "asw_shift_stack_counted", "asw_pcm16_to_f32", "asw_patch_powers",
     "asw_srp_set_frame_mode", "asw_srp_num_frames_mode", "asw_select_set_grid1", "asw_srp_set_stft_path", "asw_srp_gcc", "asw_srp_gather",
+    "asw_corr_create", "asw_corr_destroy", "asw_corr_table_len", "asw_corr_tables", "asw_shift_stack_norm_tab",
 ]
 
 
@@ -73,6 +74,11 @@ def load():
     lib.asw_srp_gather.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.asw_srp_num_frames_mode.argtypes = [i32, i32, i32, i32]
     lib.asw_patch_powers.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.asw_corr_create.argtypes = [c.POINTER(vp), i32, i32, i32]
+    lib.asw_corr_destroy.argtypes = [vp]
+    lib.asw_corr_table_len.argtypes = [vp]
+    lib.asw_corr_tables.argtypes = [vp, vp, i32, i32, vp, vp]
+    lib.asw_shift_stack_norm_tab.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name, None)
         if fn is not None and name not in ("asw_last_error", "asw_launch_count"):

@@ -15,12 +15,12 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libasw.so")
 STAMP = os.path.join(LIBDIR, "libasw.stamp")
-SOURCES = ["api.cu", "stft_cc.cu", "stft_cc_warp.cu", "gcc.cu", "srp_gather.cu", "topk.cu", "shift_stack.cu", "prune.cu", "select.cu", "geometry.cu", "powers.cu"]
+SOURCES = ["api.cu", "stft_cc.cu", "stft_cc_warp.cu", "gcc.cu", "srp_gather.cu", "topk.cu", "shift_stack.cu", "prune.cu", "select.cu", "geometry.cu", "powers.cu", "xcorr.cu"]
 # The warp-FFT kernel needs <= 128 registers/thread so that two CTAs fit the per-partition register files.
 PER_FILE_FLAGS = {"stft_cc_warp.cu": ["-maxrregcount=128"]}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--use_fast_math=false",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
 ]
 
 
@@ -57,7 +57,7 @@ def build_lib(force=False, verbose=False):
             if fh.read().strip() == dig:
                 return LIB
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = list(NVCC_FLAGS)
     if verbose:
         flags += ["-Xptxas", "-v"]
     objs = []

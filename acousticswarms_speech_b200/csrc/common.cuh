@@ -141,6 +141,7 @@ int launch_pcm16_to_f32(const short* in, float* out, size_t n, cudaStream_t s);
 int launch_shift_stack_counted(const float* mix, const int32_t* shifts, const int32_t* mix_index, const int32_t* n_valid,
                                int n_base, int N, int B, int M, int T, float* out, cudaStream_t s);
 int launch_shift_stack_norm(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int B,
-                            int M, int T, float* out, float* means, float* stds, double* work, cudaStream_t s);
+                            int M, int T, float* out, float* means, float* stds, double* work, const double* tables,
+                            int table_stride, int max_lag, cudaStream_t s);
 
 }  // namespace asw

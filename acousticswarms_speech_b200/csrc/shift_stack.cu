@@ -23,6 +23,23 @@ constexpr int kVpt = 4;  // 16-byte vectors per thread
 
 __device__ __forceinline__ float quant16(float x) { return rintf(x * 32768.f) * (1.f / 32768.f); }
 
+// round(x 2^15) without the quarter-rate FRND: for |x| < 128 the sum x 2^15 + 1.5 2^23 lands where the float spacing
+// is 1, so the FMA's round-to-nearest-even IS rintf(x 2^15) (x 2^15 itself is exact), and subtracting the constant
+// is exact.  (r 2^-15 - mean) is one more FMA with a single rounding: the same bits as fl(q - mean), q = r 2^-15.
+constexpr float kRoundMagic = 12582912.f;
+__device__ __forceinline__ float round15_small(float x) { return fmaf(x, 32768.f, kRoundMagic) - kRoundMagic; }
+__device__ __forceinline__ float4 norm4(float4 x, float mean, float inv_sd) {
+    const float big = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));
+    float4 r;
+    if (big < 128.f) {
+        r = make_float4(round15_small(x.x), round15_small(x.y), round15_small(x.z), round15_small(x.w));
+    } else {   // also NaN
+        r = make_float4(rintf(x.x * 32768.f), rintf(x.y * 32768.f), rintf(x.z * 32768.f), rintf(x.w * 32768.f));
+    }
+    return make_float4(fmaf(r.x, 1.f / 32768.f, -mean) * inv_sd, fmaf(r.y, 1.f / 32768.f, -mean) * inv_sd,
+                       fmaf(r.z, 1.f / 32768.f, -mean) * inv_sd, fmaf(r.w, 1.f / 32768.f, -mean) * inv_sd);
+}
+
 __device__ __forceinline__ int reduce_shift(int r, int T) {
     // python-style r mod T; the common case |r| < T needs no division (the XU pipe was the limiter)
     if (r <= -T || r >= T) r %= T;
@@ -63,12 +80,8 @@ __device__ __forceinline__ void shift_row_chunk(const float* __restrict__ src, f
         const int t4 = v0 + v * kThreads;
         if (t4 < T4) {
             float4 x = val[v];
-            if (NORM) {   // sd holds 1 / std here: one multiply instead of an IEEE division per sample (<= 1.5 ulp)
-                x.x = (quant16(x.x) - mean) * sd;
-                x.y = (quant16(x.y) - mean) * sd;
-                x.z = (quant16(x.z) - mean) * sd;
-                x.w = (quant16(x.w) - mean) * sd;
-            }
+            // sd holds 1 / std here: one multiply instead of an IEEE division per sample (<= 1.5 ulp)
+            if (NORM) x = norm4(x, mean, sd);
             __stcs(dst + t4, x);
         }
     }
@@ -78,8 +91,8 @@ __device__ __forceinline__ void shift_row_chunk(const float* __restrict__ src, f
 template <bool NORM>
 __global__ void __launch_bounds__(kThreads) shift_stack_vec_kernel(const float* __restrict__ mix,
                                                                     const int32_t* __restrict__ shifts,
-                                                                    const int32_t* __restrict__ mix_index, int M, int T,
-                                                                    float* __restrict__ out,
+                                                                    const int32_t* __restrict__ mix_index, int B, int M,
+                                                                    int T, float* __restrict__ out,
                                                                     const double* __restrict__ work,
                                                                     float* __restrict__ means, float* __restrict__ stds,
                                                                     const int32_t* __restrict__ n_valid, int n_base) {
@@ -91,21 +104,15 @@ __global__ void __launch_bounds__(kThreads) shift_stack_vec_kernel(const float* 
     const int mi = mix_index ? __ldg(mix_index + n) : 0;
     const int r_raw = __ldg(shifts + row);
     if (n_base + n >= nv) return;
+    if (mi < 0 || mi >= B) return;                         // stale / foreign table row: never read outside mix
     const float* src = mix + ((size_t)mi * M + c) * (size_t)T;
     float4* dst = reinterpret_cast<float4*>(out + (size_t)row * T);
     const int r = reduce_shift(r_raw, T);
     float mean = 0.f, sd = 1.f;
-    if (NORM) {
-        const double S = work[2 * n], SS = work[2 * n + 1];
-        const double mu = S / (double)T;
-        const double var = (SS - S * mu) / (double)(T - 1);
-        sd = (float)sqrt(var > 0.0 ? var : 0.0);
-        mean = (float)mu;
-        if (c == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
-            means[n] = mean;
-            stds[n] = sd;
-        }
-        sd = 1.0f / sd;                                   // shift_row_chunk multiplies
+    if (NORM) {   // {mean, 1 / std} finalised once per patch by the statistics kernel (no fp64 divide / sqrt per CTA)
+        const float2 ms = __ldg(reinterpret_cast<const float2*>(work + 2 * n));
+        mean = ms.x;
+        sd = ms.y;                                        // shift_row_chunk multiplies
     }
     switch (r & 3) {
         case 0: shift_row_chunk<NORM, 0>(src, dst, r, T, mean, sd); break;
@@ -119,8 +126,8 @@ __global__ void __launch_bounds__(kThreads) shift_stack_vec_kernel(const float* 
 template <bool NORM>
 __global__ void __launch_bounds__(kThreads) shift_stack_scalar_kernel(const float* __restrict__ mix,
                                                                        const int32_t* __restrict__ shifts,
-                                                                       const int32_t* __restrict__ mix_index, int M,
-                                                                       int T, float* __restrict__ out,
+                                                                       const int32_t* __restrict__ mix_index, int B,
+                                                                       int M, int T, float* __restrict__ out,
                                                                        const double* __restrict__ work,
                                                                        float* __restrict__ means,
                                                                        float* __restrict__ stds,
@@ -129,27 +136,22 @@ __global__ void __launch_bounds__(kThreads) shift_stack_scalar_kernel(const floa
     if (n_valid && n_base + n >= *n_valid) return;
     const int row = n * M + c;
     const int mi = mix_index ? mix_index[n] : 0;
+    if (mi < 0 || mi >= B) return;
     const float* src = mix + ((size_t)mi * M + c) * (size_t)T;
     float* dst = out + (size_t)row * T;
     const int r = reduce_shift(shifts[row], T);
     float mean = 0.f, sd = 1.f;
     if (NORM) {
-        const double S = work[2 * n], SS = work[2 * n + 1];
-        const double mu = S / (double)T;
-        const double var = (SS - S * mu) / (double)(T - 1);
-        sd = (float)sqrt(var > 0.0 ? var : 0.0);
-        mean = (float)mu;
-        if (c == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
-            means[n] = mean;
-            stds[n] = sd;
-        }
+        const float2 ms = *reinterpret_cast<const float2*>(work + 2 * n);
+        mean = ms.x;
+        sd = ms.y;                                        // 1 / std
     }
     for (int t = blockIdx.x * (kThreads * kVpt * 4) + threadIdx.x, e = min(T, (int)(blockIdx.x + 1) * (kThreads * kVpt * 4));
          t < e; t += kThreads) {
         int s = t + r;
         if (s >= T) s -= T;
         float x = __ldg(src + s);
-        if (NORM) x = (quant16(x) - mean) / sd;
+        if (NORM) x = (quant16(x) - mean) * sd;
         dst[t] = x;
     }
 }
@@ -172,18 +174,99 @@ __device__ __forceinline__ void add_quant4(float4& ref, const float* __restrict_
 // normalised sample -- are reproducible bit for bit from run to run; atomics across CTAs would not be.
 constexpr int kStatThreads = 1024;
 
+// Both moments -> what the stack pass needs: means[n], stds[n] for the caller and {mean, 1 / std} as two floats at
+// the start of the patch's work slot.
+__device__ __forceinline__ void finalise_stats(double S, double SS, int T, int n, double* __restrict__ work,
+                                               float* __restrict__ means, float* __restrict__ stds) {
+    const double mu = S / (double)T;
+    const double var = (SS - S * mu) / (double)(T - 1);
+    const float sd = (float)sqrt(var > 0.0 ? var : 0.0);
+    const float mean = (float)mu;
+    means[n] = mean;
+    stds[n] = sd;
+    *reinterpret_cast<float2*>(work + 2 * n) = make_float2(mean, 1.0f / sd);
+}
+
+// With `tables` (asw_corr_tables, xcorr.cu) the two moments come from M + M + P look-ups per patch:
+//     sum ref = 1/M sum_c S_c,   sum ref^2 = 1/M^2 (sum_c E_c + 2 sum_{c<c'} R_cc'(r_c' - r_c)),
+// and the CTA returns before touching the audio.  A patch whose lag falls outside the table, or whose centred second
+// moment is small against the fp32 round-off of the table entries (bounded through (sum_c sqrt E_c)^2 >= M^2 sum ref^2),
+// takes the exact pass below instead, so the result never depends on the table's range.
+constexpr double kTableCondition = 0.02;
+
 template <bool VEC>
 __global__ void __launch_bounds__(kStatThreads) shift_ref_stats_kernel(const float* __restrict__ mix,
                                                                         const int32_t* __restrict__ shifts,
-                                                                        const int32_t* __restrict__ mix_index, int M,
-                                                                        int T, double* __restrict__ work) {
+                                                                        const int32_t* __restrict__ mix_index, int B, int M,
+                                                                        int T, double* __restrict__ work,
+                                                                        float* __restrict__ means,
+                                                                        float* __restrict__ stds,
+                                                                        const double* __restrict__ tables,
+                                                                        int table_stride, int L) {
     __shared__ int s_r[kMaxMics];
     __shared__ double s_red[2][kStatThreads / 32];
+    __shared__ int s_done;
     const int n = blockIdx.x;
     const int mi = mix_index ? mix_index[n] : 0;
+    if (mi < 0 || mi >= B) {                                   // stale table row: leave a recognisable result, read nothing
+        if (threadIdx.x == 0) {
+            means[n] = 0.f;
+            stds[n] = 0.f;
+            *reinterpret_cast<float2*>(work + 2 * n) = make_float2(0.f, 0.f);
+        }
+        return;
+    }
     const float* src = mix + (size_t)mi * M * (size_t)T;
     if (threadIdx.x < M) s_r[threadIdx.x] = reduce_shift(shifts[n * M + threadIdx.x], T);
+    if (threadIdx.x == 0) s_done = 0;
     __syncthreads();
+    if (tables) {
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            const double* tb = tables + (size_t)mi * table_stride;
+            const int P = M * (M - 1) / 2;
+            double sS = 0.0, sE = 0.0, sA = 0.0, sR = 0.0;
+            int bad = 0;
+            if (lane < M) {
+                sS = tb[lane];
+                sE = tb[M + lane];
+                sA = sqrt(sE);
+            }
+            for (int p = lane; p < P; p += 32) {                 // pair p -> (i, j), i < j row-major (M <= 32: <= 31 steps)
+                int i = 0, rem = p;
+                while (rem >= M - 1 - i) {
+                    rem -= M - 1 - i;
+                    ++i;
+                }
+                const int j = i + 1 + rem;
+                int d = s_r[j] - s_r[i];                         // both in [0, T)
+                if (2 * d > T) d -= T;
+                if (2 * d < -T) d += T;
+                if (d < -L || d > L) bad = 1;
+                else sR += tb[2 * M + (size_t)p * (2 * L + 1) + (d + L)];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sS += __shfl_xor_sync(0xffffffffu, sS, o);
+                sE += __shfl_xor_sync(0xffffffffu, sE, o);
+                sA += __shfl_xor_sync(0xffffffffu, sA, o);
+                sR += __shfl_xor_sync(0xffffffffu, sR, o);
+                bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+            }
+            const double inv_m = 1.0 / (double)M;
+            const double S = sS * inv_m, SS = (sE + 2.0 * sR) * inv_m * inv_m;
+            const double centred = SS - S * S / (double)T;
+            const double bound = sA * sA * inv_m * inv_m;
+            if (!bad && centred > kTableCondition * bound) {
+                if (lane == 0) {
+                    finalise_stats(S, SS, T, n, work, means, stds);
+                    s_done = 1;
+                }
+            }
+        }
+        __syncthreads();
+        if (s_done) return;
+    }
     const float inv_m = 1.f / (float)M;
     double sum = 0.0, sq = 0.0;
     if (VEC) {
@@ -237,8 +320,7 @@ __global__ void __launch_bounds__(kStatThreads) shift_ref_stats_kernel(const flo
             a += s_red[0][i];
             c += s_red[1][i];
         }
-        work[2 * n] = a;
-        work[2 * n + 1] = c;
+        finalise_stats(a, c, T, n, work, means, stds);
     }
 }
 
@@ -268,7 +350,7 @@ __global__ void __launch_bounds__(256) pcm16_to_f32_kernel(const short* __restri
 }
 
 template <bool NORM>
-int launch_rows(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int M, int T, float* out,
+int launch_rows(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int B, int M, int T, float* out,
                 const double* work, float* means, float* stds, cudaStream_t s, const int32_t* n_valid = nullptr,
                 int n_base = 0) {
     const bool vec = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(mix) & 15) == 0) &&
@@ -284,10 +366,10 @@ int launch_rows(const float* mix, const int32_t* shifts, const int32_t* mix_inde
         float* mu = means ? means + n0 : nullptr;
         float* sd = stds ? stds + n0 : nullptr;
         if (vec) {
-            shift_stack_vec_kernel<NORM><<<grid, kThreads, 0, s>>>(mix, sh, mi, M, T, o, wk, mu, sd, n_valid, n_base + n0);
+            shift_stack_vec_kernel<NORM><<<grid, kThreads, 0, s>>>(mix, sh, mi, B, M, T, o, wk, mu, sd, n_valid, n_base + n0);
             ASW_LAUNCH_CHECK("shift_stack_vec_kernel");
         } else {
-            shift_stack_scalar_kernel<NORM><<<grid, kThreads, 0, s>>>(mix, sh, mi, M, T, o, wk, mu, sd, n_valid,
+            shift_stack_scalar_kernel<NORM><<<grid, kThreads, 0, s>>>(mix, sh, mi, B, M, T, o, wk, mu, sd, n_valid,
                                                                       n_base + n0);
             ASW_LAUNCH_CHECK("shift_stack_scalar_kernel");
         }
@@ -299,9 +381,8 @@ int launch_rows(const float* mix, const int32_t* shifts, const int32_t* mix_inde
 
 int launch_shift_stack(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int B, int M, int T,
                        float* out, cudaStream_t s) {
-    (void)B;
     if (N == 0) return ASW_OK;
-    return launch_rows<false>(mix, shifts, mix_index, N, M, T, out, nullptr, nullptr, nullptr, s);
+    return launch_rows<false>(mix, shifts, mix_index, N, B, M, T, out, nullptr, nullptr, nullptr, s);
 }
 
 int launch_pcm16_to_f32(const short* in, float* out, size_t n, cudaStream_t s) {
@@ -317,22 +398,23 @@ int launch_pcm16_to_f32(const short* in, float* out, size_t n, cudaStream_t s) {
 
 int launch_shift_stack_counted(const float* mix, const int32_t* shifts, const int32_t* mix_index, const int32_t* n_valid,
                                int n_base, int N, int B, int M, int T, float* out, cudaStream_t s) {
-    (void)B;
     if (N == 0) return ASW_OK;
-    return launch_rows<false>(mix, shifts + (size_t)n_base * M, mix_index + n_base, N, M, T, out, nullptr, nullptr,
+    return launch_rows<false>(mix, shifts + (size_t)n_base * M, mix_index + n_base, N, B, M, T, out, nullptr, nullptr,
                               nullptr, s, n_valid, n_base);
 }
 
 int launch_shift_stack_norm(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int B, int M,
-                            int T, float* out, float* means, float* stds, double* work, cudaStream_t s) {
-    (void)B;
+                            int T, float* out, float* means, float* stds, double* work, const double* tables,
+                            int table_stride, int max_lag, cudaStream_t s) {
     if (N == 0) return ASW_OK;
     if ((T % 4 == 0) && ((reinterpret_cast<uintptr_t>(mix) & 15) == 0))
-        shift_ref_stats_kernel<true><<<N, kStatThreads, 0, s>>>(mix, shifts, mix_index, M, T, work);
+        shift_ref_stats_kernel<true><<<N, kStatThreads, 0, s>>>(mix, shifts, mix_index, B, M, T, work, means, stds, tables,
+                                                                table_stride, max_lag);
     else
-        shift_ref_stats_kernel<false><<<N, kStatThreads, 0, s>>>(mix, shifts, mix_index, M, T, work);
+        shift_ref_stats_kernel<false><<<N, kStatThreads, 0, s>>>(mix, shifts, mix_index, B, M, T, work, means, stds, tables,
+                                                                 table_stride, max_lag);
     ASW_LAUNCH_CHECK("shift_ref_stats_kernel");
-    return launch_rows<true>(mix, shifts, mix_index, N, M, T, out, work, means, stds, s);
+    return launch_rows<true>(mix, shifts, mix_index, N, B, M, T, out, work, means, stds, s);
 }
 
 }  // namespace asw

@@ -374,6 +374,8 @@ def shift_stack_counted(mix, shifts, mix_index, n_total, n_base, N, out):
     B, M, T = mix.shape
     if shifts.shape[1] != M or out.numel() < N * M * T:
         raise _lib.AswError("shift table / output shape mismatch")
+    if n_base < 0 or n_base + N > shifts.shape[0] or n_base + N > mix_index.shape[0]:
+        raise _lib.AswError(f"rows [{n_base}, {n_base + N}) exceed the shift table's capacity {shifts.shape[0]}")
     with torch.cuda.device(mix.device):     # handle-less entry points launch on the current device
         _lib.check(_lib.load().asw_shift_stack_counted(_ptr(mix), _ptr(shifts), _ptr(mix_index), _ptr(n_total), int(n_base),
                                                        int(N), B, M, T, _ptr(out), _stream(mix.device)))
@@ -422,9 +424,63 @@ def shift_stack(mix, shifts, mix_index=None, out=None):
     return out[:N]
 
 
-def shift_stack_norm(mix, shifts, mix_index=None, out=None):
+class CorrTables:
+    """Per-mixture correlation tables (asw_corr_t) that let ``shift_stack_norm`` find a patch's mean / std from
+    M + M + P look-ups instead of a pass over its samples (see include/asw.h).  ``max_lag``: largest
+    |r_c' - r_c| the tables cover; patches beyond it fall back to the exact pass on the device."""
+
+    MIN_T = 4096
+
+    def __init__(self, num_mic, device=None, max_lag=512):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.AswError("no CUDA device: the correlation tables are CUDA-only (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.M, self.max_lag = int(num_mic), int(max_lag)
+        self._h = ctypes.c_void_p()
+        _lib.check(self.lib.asw_corr_create(ctypes.byref(self._h), self.device.index or 0, self.M, self.max_lag))
+        self.table_len = int(self.lib.asw_corr_table_len(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.asw_corr_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compute(self, mix, out=None):
+        """mix (B, M, T) or (M, T) float32 CUDA -> tables (B, table_len) float64 CUDA."""
+        if mix.dim() == 2:
+            mix = mix.unsqueeze(0)
+        _require_cuda(mix, "mix", torch.float32)
+        B, M, T = mix.shape
+        if M != self.M:
+            raise _lib.AswError(f"mix has {M} channels, handle was built for {self.M}")
+        if out is None:
+            out = torch.empty((B, self.table_len), device=mix.device, dtype=torch.float64)
+        else:
+            _require_cuda(out, "out", torch.float64)
+            if out.numel() < B * self.table_len:
+                raise _lib.AswError("out is too small")
+        _lib.check(self.lib.asw_corr_tables(self._h, _ptr(mix), B, T, _ptr(out), _stream(mix.device)))
+        return out
+
+    def pair_table(self, tables, b, i, j):
+        """R_ij(l), l = -max_lag..max_lag, of mixture b (i < j) as a (2 max_lag + 1,) view."""
+        p = i * self.M - i * (i + 1) // 2 + (j - i - 1)
+        n = 2 * self.max_lag + 1
+        return tables[b, 2 * self.M + p * n: 2 * self.M + (p + 1) * n]
+
+
+def shift_stack_norm(mix, shifts, mix_index=None, out=None, tables=None, max_lag=0):
     """shift_stack fused with normalize_input (SpeakerLocalization/network.py:28-40).
-    Returns (data_norm (N, M, T), means (N, 1, 1), stds (N, 1, 1))."""
+    Returns (data_norm (N, M, T), means (N, 1, 1), stds (N, 1, 1)).
+    ``tables`` (B, table_len) float64 from ``CorrTables.compute`` (+ its ``max_lag``): the statistics come from the
+    per-mixture tables (asw_shift_stack_norm_tab) instead of a pass over every patch."""
     if mix.dim() == 2:
         mix = mix.unsqueeze(0)
     _require_cuda(mix, "mix", torch.float32)
@@ -444,11 +500,18 @@ def shift_stack_norm(mix, shifts, mix_index=None, out=None):
     work = torch.empty((N, 2), device=mix.device, dtype=torch.float64)
     if N == 0:
         return out[:0], means.view(0, 1, 1), stds.view(0, 1, 1)
+    mip = _ptr(mix_index) if mix_index is not None else None
     with torch.cuda.device(mix.device):     # handle-less entry points launch on the current device
-        _lib.check(_lib.load().asw_shift_stack_norm(_ptr(mix), _ptr(shifts),
-                                                    _ptr(mix_index) if mix_index is not None else None, N, B, M, T,
-                                                    _ptr(out), _ptr(means), _ptr(stds), _ptr(work),
-                                                    _stream(mix.device)))
+        if tables is not None:
+            _require_cuda(tables, "tables", torch.float64)
+            if tables.dim() != 2 or tables.shape[0] != B:
+                raise _lib.AswError("tables must be (B, table_len)")
+            _lib.check(_lib.load().asw_shift_stack_norm_tab(_ptr(mix), _ptr(shifts), mip, N, B, M, T, _ptr(tables),
+                                                            int(tables.shape[1]), int(max_lag), _ptr(out), _ptr(means),
+                                                            _ptr(stds), _ptr(work), _stream(mix.device)))
+        else:
+            _lib.check(_lib.load().asw_shift_stack_norm(_ptr(mix), _ptr(shifts), mip, N, B, M, T, _ptr(out),
+                                                        _ptr(means), _ptr(stds), _ptr(work), _stream(mix.device)))
     return out[:N], means.view(N, 1, 1), stds.view(N, 1, 1)
 
 

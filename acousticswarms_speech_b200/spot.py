@@ -66,6 +66,9 @@ def si_sdr_from_gram(ee, rr, er):
 
 
 class DataParallelSpotModel(nn.Module):
+    TABLE_MIN_PATCHES = 48      # below this the exact per-patch statistics pass is cheaper than building the tables
+    TABLE_MAX_LAG = 512         # samples; patches with a larger pair lag take the exact pass on the device
+
     def __init__(self, model, use_fp16=False, batch_size=SPOT_BATCH_SIZE, device=None, data_parallel=True):
         super().__init__()
         multi = data_parallel and torch.cuda.device_count() > 1
@@ -77,6 +80,7 @@ class DataParallelSpotModel(nn.Module):
         self._device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.to(self._device)
         self._buf = None
+        self._corr = None
 
     @property
     def device(self):
@@ -98,10 +102,18 @@ class DataParallelSpotModel(nn.Module):
             cond[:, 0 if Strict == 1 else 1] = 1                                  # :62-73
             shifts = torch.from_numpy(native.offsets_to_shifts(
                 np.stack([p.sample_offset for p in patch_list]) if N else np.zeros((0, M - 1)))).to(dev)
+            # per-mixture correlation tables: every patch's mean / std from a few look-ups instead of a pass over its
+            # samples (pays off from a few dozen patches on; fewer take the exact statistics pass)
+            tables = None
+            if N >= self.TABLE_MIN_PATCHES and T >= native.CorrTables.MIN_T and M >= 2:
+                if self._corr is None or self._corr.M != M:
+                    self._corr = native.CorrTables(M, dev, max_lag=self.TABLE_MAX_LAG)
+                tables = self._corr.compute(mix)
             saved = []
             for i in range(0, N, B):
                 n = min(B, N - i)
-                data_norm, means, stds = native.shift_stack_norm(mix, shifts[i:i + n], out=self._buf)
+                data_norm, means, stds = native.shift_stack_norm(mix, shifts[i:i + n], out=self._buf, tables=tables,
+                                                                 max_lag=self.TABLE_MAX_LAG)
                 data_norm = data_norm[:n]
                 if save_input:
                     saved.append(unnormalize_input(data_norm, means, stds).cpu())

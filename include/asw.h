@@ -162,7 +162,8 @@ int asw_patch_powers(float* x_dev, int N, int T, int window, int demean, float* 
  * mod T with Python semantics).
  *   mix_dev    [B][M][T] float32
  *   shifts_dev [N][M] int32
- *   mix_index_dev [N] int32 or NULL (all patches read mixture 0)
+ *   mix_index_dev [N] int32 or NULL (all patches read mixture 0); a row whose index is outside [0, B) is
+ *                 skipped (its output slot is left untouched), never read out of bounds
  *   out_dev    [N][M][T] float32 -- the network's input layout (batch, mic, time) */
 int asw_shift_stack(const float* mix_dev, const int32_t* shifts_dev, const int32_t* mix_index_dev,
                     int N, int B, int M, int T, float* out_dev, void* stream);
@@ -177,6 +178,32 @@ int asw_shift_stack(const float* mix_dev, const int32_t* shifts_dev, const int32
 int asw_shift_stack_norm(const float* mix_dev, const int32_t* shifts_dev, const int32_t* mix_index_dev,
                          int N, int B, int M, int T, float* out_dev, float* means_dev, float* stds_dev,
                          double* work_dev, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Per-mixture correlation tables for the fused normalize_input
+ * (sep/training/SpeakerLocalization/network.py:28-40 applied to the shifted stack of
+ * sep/training/JointModel/network.py:75-85).  The mean and the unbiased std of a patch's mic-average
+ *     ref[t] = 1/M sum_c q_c[(t + r_c) mod T],   q = round(x 2^15) / 2^15
+ * are functions of per-mixture sums:  sum ref = 1/M sum_c S_c  and
+ *     sum ref^2 = 1/M^2 (sum_c E_c + 2 sum_{c<c'} R_cc'(r_c' - r_c)),  R_cc'(l) = sum_t q_c[t] q_c'[(t+l) mod T].
+ * asw_corr_tables computes, per mixture, S_c [M], E_c [M] and R_cc'(l) [P][2 max_lag + 1] (pairs i<j row-major,
+ * l = -max_lag..max_lag) as float64 (S, E exact; R by overlap-save FFT correlation in fp32, ~3e-7 sqrt(E_c E_c')).
+ * asw_shift_stack_norm_tab then needs M + M + P look-ups per patch instead of a pass over its M T samples; a patch
+ * whose pair lag exceeds max_lag, or whose variance is small against the table's round-off, silently takes the
+ * exact pass of asw_shift_stack_norm, so the result does not depend on max_lag.  Means / stds agree with the exact
+ * pass to ~1e-6 relative (bar: 1e-4); results are reproducible bit for bit.
+ *   asw_corr_create: max_lag in 1..512 samples (48 kHz: 3.6 m of aperture); M in 2..32
+ *   asw_corr_tables: mix_dev [B][M][T] float32, T >= 4096; tables_dev [B][asw_corr_table_len] float64 out.
+ * The handle owns the spectrum workspace (<= 48 MB: the batch is processed in L2-sized chunks); it is
+ * single-stream and not re-entrant. */
+typedef struct asw_corr asw_corr_t;
+int asw_corr_create(asw_corr_t** out, int device, int M, int max_lag);
+int asw_corr_destroy(asw_corr_t* h);
+int asw_corr_table_len(const asw_corr_t* h);
+int asw_corr_tables(asw_corr_t* h, const float* mix_dev, int B, int T, double* tables_dev, void* stream);
+int asw_shift_stack_norm_tab(const float* mix_dev, const int32_t* shifts_dev, const int32_t* mix_index_dev,
+                             int N, int B, int M, int T, const double* tables_dev, int table_len, int max_lag,
+                             float* out_dev, float* means_dev, float* stds_dev, double* work_dev, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Peak picking on the device: fill_powermap_torch + MAX_POWER + find_valid_peak_new

@@ -121,3 +121,109 @@ def test_pcm16_ingest_is_exact(cuda_device):
             pcm[:4] = [-32768, 32767, 0, -1]
         got = native.pcm16_to_f32(torch.from_numpy(pcm).cuda()).cpu().numpy()
         assert np.array_equal(got, pcm.astype(np.float32) / np.float32(32768.0))
+
+
+# ---- correlation tables (asw_corr_tables) and the table-driven fused normalize (asw_shift_stack_norm_tab) ----------
+def _circ_corr(a, b, lag):
+    """sum_t a[t] b[(t + lag) mod T] in float64."""
+    return float(np.dot(a, np.roll(b, -lag)))
+
+
+@pytest.mark.parametrize("M,T,L", [(3, 8192, 512), (7, 144000, 512), (4, 132300, 300), (2, 4099, 100)])
+def test_corr_tables_match_direct_correlation(cuda_device, M, T, L):
+    """S_c, E_c exact; R_cc'(l) within fp32-FFT round-off of the float64 circular correlation of the re-quantised
+    channels, for every pair at the table's edges and at random lags (T odd exercises the scalar loader, the last
+    block is ragged for every T here)."""
+    from acousticswarms_speech_b200 import native
+    rng = np.random.default_rng(M * 1000 + L)
+    B = 2
+    mix = (0.2 * rng.standard_normal((B, M, T))).astype(np.float32)
+    mix[1, 0] += 0.05                                   # a DC offset on one channel
+    ct = native.CorrTables(M, cuda_device, max_lag=L)
+    tab = ct.compute(torch.from_numpy(mix).to(cuda_device)).cpu().numpy()
+    assert tab.shape == (B, 2 * M + (M * (M - 1) // 2) * (2 * L + 1))
+    q = (np.rint(mix * np.float32(32768.0)) / np.float32(32768.0)).astype(np.float64)
+    worst = 0.0
+    for b in range(B):
+        assert np.allclose(tab[b, :M], q[b].sum(1), rtol=0, atol=1e-9)
+        assert np.allclose(tab[b, M:2 * M], (q[b] ** 2).sum(1), rtol=1e-13, atol=0)
+        p = 0
+        for i in range(M):
+            for j in range(i + 1, M):
+                row = tab[b, 2 * M + p * (2 * L + 1): 2 * M + (p + 1) * (2 * L + 1)]
+                scale = np.sqrt((q[b, i] ** 2).sum() * (q[b, j] ** 2).sum())
+                for lag in [-L, -L + 1, -1, 0, 1, L - 1, L] + list(rng.integers(-L, L + 1, size=6)):
+                    worst = max(worst, abs(row[lag + L] - _circ_corr(q[b, i], q[b, j], int(lag))) / scale)
+                p += 1
+    print(f"corr tables M={M} T={T} L={L}: worst |dR| / sqrt(E_i E_j) = {worst:.2e}")
+    assert worst <= 2e-6
+
+
+def test_shift_stack_norm_tab_matches_exact_pass(cuda_device):
+    """Table-driven statistics vs the exact pass and vs the oracle: means / stds within 1e-6 relative of the exact
+    pass, normalised samples within 1e-5, oracle bar 1e-4; a patch whose lag exceeds the table takes the exact pass
+    on the device and is then bit-identical to it; results are reproducible bit for bit."""
+    from acousticswarms_speech_b200 import native
+    rng = np.random.default_rng(21)
+    B, M, T, N, L = 3, 7, 144000, 48, 512
+    t = np.arange(T)
+    mix = np.zeros((B, M, T), dtype=np.float32)
+    for b in range(B):                                   # correlated channels: a common source at different delays + noise
+        src = np.convolve(rng.standard_normal(T + 600), np.hanning(9), mode="same")
+        for c in range(M):
+            d = int(rng.integers(0, 300))
+            mix[b, c] = 0.05 * src[d:d + T] + 0.01 * rng.standard_normal(T)
+    shifts = rng.integers(-250, 251, size=(N, M)).astype(np.int32)
+    shifts[:, 0] = 0
+    shifts[5, 3] = 700                                   # |r_3 - r_c| > L: exact pass for this patch
+    shifts[6] = shifts[6] + T                            # shifts beyond T reduce mod T
+    shifts[6, 0] = 0
+    mi = rng.integers(0, B, size=N).astype(np.int32)
+    x = torch.from_numpy(mix).to(cuda_device)
+    sh, mid = torch.from_numpy(shifts).to(cuda_device), torch.from_numpy(mi).to(cuda_device)
+    ct = native.CorrTables(M, cuda_device, max_lag=L)
+    tab = ct.compute(x)
+    exact = [v.clone() for v in native.shift_stack_norm(x, sh, mid)]
+    fast = [v.clone() for v in native.shift_stack_norm(x, sh, mid, tables=tab, max_lag=L)]
+    again = native.shift_stack_norm(x, sh, mid, tables=ct.compute(x), max_lag=L)
+    assert all(torch.equal(a, b) for a, b in zip(fast, again)), "table path is not reproducible"
+    mu_e, sd_e = exact[1].cpu().numpy().ravel(), exact[2].cpu().numpy().ravel()
+    mu_f, sd_f = fast[1].cpu().numpy().ravel(), fast[2].cpu().numpy().ravel()
+    rel_sd = np.abs(sd_f - sd_e) / sd_e
+    print(f"norm_tab: max rel std diff {rel_sd.max():.2e}, max |mean diff| / std {np.abs(mu_f - mu_e).max() / sd_e.min():.2e}")
+    assert rel_sd.max() <= 1e-6
+    assert np.abs(mu_f - mu_e).max() <= 1e-6 * sd_e.min()
+    assert torch.equal(fast[0][5], exact[0][5]) and sd_f[5] == sd_e[5], "out-of-table patch must take the exact pass"
+    dn_e, dn_f = exact[0].cpu().numpy(), fast[0].cpu().numpy()
+    assert np.abs(dn_f - dn_e).max() <= 1e-5 * np.abs(dn_e).max()
+    for n in (0, 5, 6, N - 1):
+        want, wmu, wsd = shift_oracle.normalize_input(shift_oracle.roll_by_gather(mix[mi[n]], -shifts[n].astype(np.int64))[None])
+        assert abs(sd_f[n] - wsd.ravel()[0]) <= 1e-4 * wsd.ravel()[0]
+        assert np.abs(dn_f[n] - want[0]).max() <= 1e-4 * np.abs(want).max()
+
+
+def test_shift_stack_norm_tab_ill_conditioned_patch_takes_exact_pass(cuda_device):
+    """Channels that cancel in the mic-average (variance far below the table's round-off bound) must not be
+    normalised from the tables."""
+    from acousticswarms_speech_b200 import native
+    rng = np.random.default_rng(22)
+    M, T, L = 2, 16384, 64
+    a = (0.1 * rng.standard_normal(T)).astype(np.float32)
+    mix = np.stack([a, -a + (1e-4 * rng.standard_normal(T)).astype(np.float32)])[None]
+    x = torch.from_numpy(mix).to(cuda_device)
+    sh = torch.zeros((1, M), dtype=torch.int32, device=cuda_device)
+    ct = native.CorrTables(M, cuda_device, max_lag=L)
+    exact = native.shift_stack_norm(x, sh)
+    fast = native.shift_stack_norm(x, sh, tables=ct.compute(x), max_lag=L)
+    assert all(torch.equal(p, q) for p, q in zip(exact, fast))
+
+
+def test_shift_stack_skips_rows_with_foreign_mixture_index(cuda_device):
+    from acousticswarms_speech_b200 import native
+    B, M, T = 2, 3, 4096
+    x = torch.randn((B, M, T), device=cuda_device)
+    sh = torch.zeros((3, M), dtype=torch.int32, device=cuda_device)
+    mi = torch.tensor([0, 7, -1], dtype=torch.int32, device=cuda_device)
+    out = torch.full((3, M, T), 123.0, device=cuda_device)
+    native.shift_stack(x, sh, mi, out=out)
+    assert torch.equal(out[0], x[0]) and bool((out[1:] == 123.0).all())
