@@ -692,23 +692,24 @@ int asw_shift_stack_norm(const float* mix_dev, const int32_t* shifts_dev, const 
         return ASW_ERR_ARG;
     }
     return launch_shift_stack_norm(mix_dev, shifts_dev, mix_index_dev, N, B, M, T, out_dev, means_dev, stds_dev,
-                                   work_dev, nullptr, 0, 0, (cudaStream_t)stream);
+                                   work_dev, nullptr, 0, 0, nullptr, 0, (cudaStream_t)stream);
 }
 
 int asw_shift_stack_norm_tab(const float* mix_dev, const int32_t* shifts_dev, const int32_t* mix_index_dev, int N, int B,
                              int M, int T, const double* tables_dev, int table_len, int max_lag, float* out_dev,
-                             float* means_dev, float* stds_dev, double* work_dev, void* stream) {
-    if (!mix_dev || !shifts_dev || !out_dev || !means_dev || !stds_dev || !work_dev || !tables_dev || N < 0 || B < 1 ||
-        M < 2 || M > kMaxMics || T < 2) {
+                             float* means_dev, float* stds_dev, double* work_dev, const int32_t* n_valid_dev, int n_base,
+                             void* stream) {
+    if (!mix_dev || !shifts_dev || !out_dev || !means_dev || !stds_dev || !work_dev || N < 0 || B < 1 || M < 1 ||
+        M > kMaxMics || T < 2 || n_base < 0) {
         set_error("asw_shift_stack_norm_tab: null buffer or bad shape (N=%d B=%d M=%d T=%d)", N, B, M, T);
         return ASW_ERR_ARG;
     }
-    if (max_lag < 1 || table_len != 2 * M + (M * (M - 1) / 2) * (2 * max_lag + 1)) {
+    if (tables_dev && (M < 2 || max_lag < 1 || table_len != 2 * M + (M * (M - 1) / 2) * (2 * max_lag + 1))) {
         set_error("asw_shift_stack_norm_tab: table_len=%d does not belong to M=%d, max_lag=%d", table_len, M, max_lag);
         return ASW_ERR_ARG;
     }
     return launch_shift_stack_norm(mix_dev, shifts_dev, mix_index_dev, N, B, M, T, out_dev, means_dev, stds_dev,
-                                   work_dev, tables_dev, table_len, max_lag, (cudaStream_t)stream);
+                                   work_dev, tables_dev, table_len, max_lag, n_valid_dev, n_base, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -433,6 +433,14 @@ __global__ void __launch_bounds__(kSubThreads) subdivide_kernel(SubParams q) {
     int32_t* area = q.lists + (size_t)cand * 3 * kListCap;
     int32_t* buf[2] = {area + kListCap, area + 2 * kListCap};
     const int wc = q.widths[cand];
+    if (wc <= 0) {                    // empty slot of a padded candidate list (batched callers): nothing to subdivide
+        if (tid == 0) {
+            q.leaf_count[cand] = 0;
+            q.status[cand] = 0;
+            if (q.root_count) q.root_count[cand] = 0;
+        }
+        return;
+    }
 
     // ---- member voxels of the coarse patch: hyperbola_area_init (SRP_Prunning.py:41-61), unordered
     if (tid < D) {
@@ -775,6 +783,80 @@ __global__ void build_shift_table_kernel(const int32_t* __restrict__ cnt, const 
     }
 }
 
+// Fine-stage shift table (the patch-list assembly of Spotform_Small_Patch_Parallel, sep/Mic_Array.py:244-262): every
+// candidate contributes its leaves followed by one centre patch at its own (checked-out) offsets.
+// Kernel 1: exclusive prefix of the row counts (one CTA, chunks of 1024 candidates); kernel 2: one CTA per candidate.
+__global__ void __launch_bounds__(1024) fine_table_prefix_kernel(const int32_t* __restrict__ leaf_count,
+                                                                  const int32_t* __restrict__ widths, int n,
+                                                                  int max_leaves, int32_t* __restrict__ cand_start,
+                                                                  int32_t* __restrict__ n_total, int cap) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        int rows = 0;
+        if (i < n && widths[i] > 0) rows = min(leaf_count[i], max_leaves) + 1;
+        int incl = rows;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += v;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int before = s_carry + (warp ? s_warp[warp - 1] : 0) + incl - rows;
+        if (i < n) cand_start[i] = before;
+        __syncthreads();
+        if (tid == 1023) s_carry = before + rows;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        cand_start[n] = s_carry;
+        *n_total = s_carry < cap ? s_carry : cap;
+    }
+}
+
+__global__ void __launch_bounds__(128) fine_table_rows_kernel(const int32_t* __restrict__ leaf_count,
+                                                               const int32_t* __restrict__ leaf_off,
+                                                               const int32_t* __restrict__ root_after,
+                                                               const int32_t* __restrict__ owner,
+                                                               const int32_t* __restrict__ cand_start, int max_leaves,
+                                                               int D, int32_t* __restrict__ shifts,
+                                                               int32_t* __restrict__ mix_index,
+                                                               int32_t* __restrict__ cand_index, int cap) {
+    const int i = blockIdx.x;
+    const int s0 = cand_start[i], rows = cand_start[i + 1] - s0;
+    if (rows <= 0) return;
+    const int M = D + 1, leaves = rows - 1;
+    const int own = owner ? owner[i] : 0;
+    for (int k = threadIdx.x; k < rows * M; k += blockDim.x) {
+        const int q = k / M, ch = k - q * M;
+        const int nrow = s0 + q;
+        if (nrow >= cap) continue;
+        int v = 0;
+        if (ch > 0)
+            v = q < leaves ? leaf_off[((size_t)i * max_leaves + q) * D + ch - 1] : root_after[(size_t)i * 2 * D + ch - 1];
+        shifts[(size_t)nrow * M + ch] = v;
+        if (ch == 0) {
+            mix_index[nrow] = own;
+            if (cand_index) cand_index[nrow] = i;
+        }
+    }
+}
+
 }  // namespace
 }  // namespace asw
 
@@ -1016,6 +1098,25 @@ int asw_subdivide(asw_select_t* h, const int32_t* centres_dev, const int32_t* wi
     }
     subdivide_kernel<<<n, kSubThreads, smem, (cudaStream_t)stream>>>(q);
     ASW_LAUNCH_CHECK("subdivide_kernel");
+    return ASW_OK;
+}
+
+int asw_build_fine_table(const int32_t* leaf_count_dev, const int32_t* leaf_off_dev, const int32_t* root_after_dev,
+                         const int32_t* widths_dev, const int32_t* owner_dev, int n, int max_leaves, int D,
+                         int32_t* shifts_dev, int32_t* mix_index_dev, int32_t* cand_index_dev, int32_t* cand_start_dev,
+                         int32_t* n_total_dev, int capacity, void* stream) {
+    if (!leaf_count_dev || !leaf_off_dev || !root_after_dev || !widths_dev || !shifts_dev || !mix_index_dev ||
+        !cand_start_dev || !n_total_dev || n < 1 || max_leaves < 1 || D < 1 || capacity < 1) {
+        set_error("asw_build_fine_table: null argument or bad shape");
+        return ASW_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    fine_table_prefix_kernel<<<1, 1024, 0, s>>>(leaf_count_dev, widths_dev, n, max_leaves, cand_start_dev, n_total_dev,
+                                                capacity);
+    ASW_LAUNCH_CHECK("fine_table_prefix_kernel");
+    fine_table_rows_kernel<<<n, 128, 0, s>>>(leaf_count_dev, leaf_off_dev, root_after_dev, owner_dev, cand_start_dev,
+                                             max_leaves, D, shifts_dev, mix_index_dev, cand_index_dev, capacity);
+    ASW_LAUNCH_CHECK("fine_table_rows_kernel");
     return ASW_OK;
 }
 

@@ -202,11 +202,13 @@ __global__ void __launch_bounds__(kStatThreads) shift_ref_stats_kernel(const flo
                                                                         float* __restrict__ means,
                                                                         float* __restrict__ stds,
                                                                         const double* __restrict__ tables,
-                                                                        int table_stride, int L) {
+                                                                        int table_stride, int L,
+                                                                        const int32_t* __restrict__ n_valid, int n_base) {
     __shared__ int s_r[kMaxMics];
     __shared__ double s_red[2][kStatThreads / 32];
     __shared__ int s_done;
     const int n = blockIdx.x;
+    if (n_valid && n_base + n >= *n_valid) return;             // beyond the device-resident patch count
     const int mi = mix_index ? mix_index[n] : 0;
     if (mi < 0 || mi >= B) {                                   // stale table row: leave a recognisable result, read nothing
         if (threadIdx.x == 0) {
@@ -405,16 +407,18 @@ int launch_shift_stack_counted(const float* mix, const int32_t* shifts, const in
 
 int launch_shift_stack_norm(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int B, int M,
                             int T, float* out, float* means, float* stds, double* work, const double* tables,
-                            int table_stride, int max_lag, cudaStream_t s) {
+                            int table_stride, int max_lag, const int32_t* n_valid, int n_base, cudaStream_t s) {
     if (N == 0) return ASW_OK;
+    shifts += (size_t)n_base * M;
+    if (mix_index) mix_index += n_base;
     if ((T % 4 == 0) && ((reinterpret_cast<uintptr_t>(mix) & 15) == 0))
         shift_ref_stats_kernel<true><<<N, kStatThreads, 0, s>>>(mix, shifts, mix_index, B, M, T, work, means, stds, tables,
-                                                                table_stride, max_lag);
+                                                                table_stride, max_lag, n_valid, n_base);
     else
         shift_ref_stats_kernel<false><<<N, kStatThreads, 0, s>>>(mix, shifts, mix_index, B, M, T, work, means, stds, tables,
-                                                                 table_stride, max_lag);
+                                                                 table_stride, max_lag, n_valid, n_base);
     ASW_LAUNCH_CHECK("shift_ref_stats_kernel");
-    return launch_rows<true>(mix, shifts, mix_index, N, B, M, T, out, work, means, stds, s);
+    return launch_rows<true>(mix, shifts, mix_index, N, B, M, T, out, work, means, stds, s, n_valid, n_base);
 }
 
 }  // namespace asw

@@ -33,21 +33,23 @@ def max_avg_power(x, window_size=12000):
     return e.max(), np.pad(x, (0, window_size))[y:y + window_size]
 
 
-def _tdoa_rows(points, mic_positions):
+def _tdoa_rows(points, mic_positions, fs=FS):
+    """TDoA (samples at ``fs``) of every point to mics 1.. vs mic 0 (:220-224; the reference hard-codes 48 kHz)."""
     d0 = (((points[0, :] - mic_positions[0, 0]) ** 2 + (points[1, :] - mic_positions[0, 1]) ** 2
-           + (points[2, :] - mic_positions[0, 2]) ** 2) ** 0.5) / SPEED_OF_SOUND * FS
+           + (points[2, :] - mic_positions[0, 2]) ** 2) ** 0.5) / SPEED_OF_SOUND * fs
     rows = []
     for i in range(mic_positions.shape[0] - 1):
         di = (((points[0, :] - mic_positions[i + 1, 0]) ** 2 + (points[1, :] - mic_positions[i + 1, 1]) ** 2
-               + (points[2, :] - mic_positions[i + 1, 2]) ** 2) ** 0.5) / SPEED_OF_SOUND * FS
+               + (points[2, :] - mic_positions[i + 1, 2]) ** 2) ** 0.5) / SPEED_OF_SOUND * fs
         rows.append(di - d0)
     return np.array(rows)
 
 
-def search_area(patch_list, mic_positions, upper_bound_pairwise):
-    """Recursively halve a coarse hypercube until every dimension is fine enough (:212-246)."""
+def search_area(patch_list, mic_positions, upper_bound_pairwise, fs=FS):
+    """Recursively halve a coarse hypercube until every dimension is fine enough (:212-246).  ``fs``: the sampling
+    rate the patches' offsets are expressed in (the reference's constant 48 kHz by default)."""
     finished = []
-    samples_lists = [_tdoa_rows(patch_list[0].area_points, mic_positions)]
+    samples_lists = [_tdoa_rows(patch_list[0].area_points, mic_positions, fs)]
     while True:
         next_patches, next_samples = [], []
         for i, patch in enumerate(patch_list):

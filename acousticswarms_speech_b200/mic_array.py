@@ -32,16 +32,17 @@ def weight_mean_pos(patch_list, powers, id_lists):
     return total_pos / total_power, total_offsets / total_power
 
 
-def find_merge_center(merged_offests, init_area, mic_positions, Big_patch_center):
-    """Mic_Array.py:50-81 (the widening loop only ever tries factor 0, as in the reference)."""
+def find_merge_center(merged_offests, init_area, mic_positions, Big_patch_center, fs=FS):
+    """Mic_Array.py:50-81 (the widening loop only ever tries factor 0, as in the reference).  ``fs``: the rate the
+    offsets are in (the reference hard-codes 48 kHz)."""
     num_pair = mic_positions.shape[0] - 1
     patch_center = Patch(merged_offests, [3 for _ in range(num_pair)], None)
     area = patch_center.hyperbola_general_area(init_area[0, :], init_area[1, :], init_area[2, :], mic_positions,
-                                               SPEED_OF_SOUND, FS) == 1
+                                               SPEED_OF_SOUND, fs) == 1
     if np.sum(area) == 0:
         patch_center.width_list = [3 for _ in range(num_pair)]
         area = patch_center.hyperbola_general_area(init_area[0, :], init_area[1, :], init_area[2, :],
-                                                   mic_positions, SPEED_OF_SOUND, FS) == 1
+                                                   mic_positions, SPEED_OF_SOUND, fs) == 1
         if np.sum(area) > 0:
             patch_center.area_points = init_area[:, area]
         else:
@@ -135,7 +136,7 @@ class Mic_Array(object):
                 def build():
                     area = parent()
                     if "rows" not in cache:              # the candidate's TDoA rows, once for all its leaves
-                        cache["rows"] = _tdoa_rows(area, self.mic_positions)
+                        cache["rows"] = _tdoa_rows(area, self.mic_positions, self.fs)
                     rows = cache["rows"]
                     keep = np.all((rows >= lo[:, None]) & (rows <= hi[:, None]), axis=0)
                     return area[:, keep]
@@ -159,7 +160,7 @@ class Mic_Array(object):
             if on_device:
                 patch_processed = fine_lists[ci]
             else:
-                patch_processed = search_area([cand], self.mic_positions, self.upper_bound_pairwise)
+                patch_processed = search_area([cand], self.mic_positions, self.upper_bound_pairwise, self.fs)
             init_area_total.append(cand.area_points_getter())    # (:246) materialised only for clusters that are output
             patch_center0 = Patch(cand.sample_offset, width_list0, None, cand.peak_pos)
             centre = patch_center0.center_pos()
@@ -247,7 +248,7 @@ class Mic_Array(object):
                     clusters[_id] = [_id]
             for cluster_id in clusters:
                 position, offests = weight_mean_pos(patch_processed, powers, clusters[cluster_id])
-                patch_center = find_merge_center(offests, init_area(), self.mic_positions, Big_patch_center)
+                patch_center = find_merge_center(offests, init_area(), self.mic_positions, Big_patch_center, self.fs)
                 save_offsets = {"audio_offset": patch_processed[cluster_id].sample_offset,
                                 "localization_offset": offests}
                 audio = rows.row(lo + cluster_id) if rows is not None else sep_data[cluster_id, :]

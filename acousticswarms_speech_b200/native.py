@@ -343,6 +343,55 @@ def subdivide(select_handle, centres, widths, upper_bound, max_leaves=128, membe
     return out + ([srt[i, :rc[i]].astype(np.int64) for i in range(n)],)
 
 
+def subdivide_device(select_handle, centres, widths, upper_bound, max_leaves=128):
+    """``subdivide`` without the host round trip: device tensors (leaf_count (n,), leaf_off (n, L, D), leaf_w (n, L, D),
+    root_after (n, 2, D), status (n,)).  Candidates with ``widths <= 0`` are empty slots (leaf_count 0).  The caller
+    checks ``status`` / ``leaf_count <= max_leaves`` when it next synchronises."""
+    _require_cuda(centres, "centres", torch.int32)
+    _require_cuda(widths, "widths", torch.int32)
+    n, D = centres.shape
+    dev = centres.device
+    ub = np.ascontiguousarray(upper_bound, dtype=np.float64)
+    if ub.shape != (D,):
+        raise _lib.AswError(f"upper_bound must have {D} entries")
+    cnt = torch.zeros((n,), device=dev, dtype=torch.int32)
+    off = torch.empty((n, max_leaves, D), device=dev, dtype=torch.int32)
+    wid = torch.empty((n, max_leaves, D), device=dev, dtype=torch.int32)
+    npts = torch.empty((n, max_leaves), device=dev, dtype=torch.int32)
+    box = torch.empty((n, max_leaves, 2, D), device=dev, dtype=torch.float64)
+    root = torch.zeros((n, 2, D), device=dev, dtype=torch.int32)
+    status = torch.zeros((n,), device=dev, dtype=torch.int32)
+    if n:
+        _lib.check(select_handle.lib.asw_subdivide(select_handle._h, _ptr(centres), _ptr(widths), n, ub.ctypes.data,
+                                                   int(max_leaves), _ptr(cnt), _ptr(off), _ptr(wid), _ptr(npts),
+                                                   _ptr(box), None, _ptr(root), _ptr(status), None, 0, None,
+                                                   _stream(dev)))
+    return cnt, off, wid, root, status
+
+
+def build_fine_table(leaf_count, leaf_off, root_after, widths, owner, capacity):
+    """asw_build_fine_table: -> (shifts (capacity, D + 1), mix_index (capacity,), cand_index (capacity,),
+    cand_start (n + 1,), n_total (1,)), all int32 CUDA, no host synchronisation."""
+    for t, name in ((leaf_count, "leaf_count"), (leaf_off, "leaf_off"), (root_after, "root_after"), (widths, "widths")):
+        _require_cuda(t, name, torch.int32)
+    if owner is not None:
+        _require_cuda(owner, "owner", torch.int32)
+    n, L, D = leaf_off.shape
+    dev = leaf_off.device
+    shifts = torch.zeros((capacity, D + 1), device=dev, dtype=torch.int32)
+    mix_index = torch.zeros((capacity,), device=dev, dtype=torch.int32)
+    cand_index = torch.zeros((capacity,), device=dev, dtype=torch.int32)
+    cand_start = torch.zeros((n + 1,), device=dev, dtype=torch.int32)
+    n_total = torch.zeros((1,), device=dev, dtype=torch.int32)
+    if n:
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().asw_build_fine_table(_ptr(leaf_count), _ptr(leaf_off), _ptr(root_after), _ptr(widths),
+                                                        _ptr(owner) if owner is not None else None, n, L, D,
+                                                        _ptr(shifts), _ptr(mix_index), _ptr(cand_index),
+                                                        _ptr(cand_start), _ptr(n_total), int(capacity), _stream(dev)))
+    return shifts, mix_index, cand_index, cand_start, n_total
+
+
 def build_shift_table(n_patches, offsets, capacity, shifts=None, mix_index=None, n_total=None):
     """Per-mixture patch lists -> dense (capacity, D + 1) int32 shift table, (capacity,) mixture index and the
     device-resident total, without leaving the device."""
@@ -476,19 +525,29 @@ class CorrTables:
         return tables[b, 2 * self.M + p * n: 2 * self.M + (p + 1) * n]
 
 
-def shift_stack_norm(mix, shifts, mix_index=None, out=None, tables=None, max_lag=0):
+def shift_stack_norm(mix, shifts, mix_index=None, out=None, tables=None, max_lag=0, n_total=None, n_base=0, N=None):
     """shift_stack fused with normalize_input (SpeakerLocalization/network.py:28-40).
     Returns (data_norm (N, M, T), means (N, 1, 1), stds (N, 1, 1)).
     ``tables`` (B, table_len) float64 from ``CorrTables.compute`` (+ its ``max_lag``): the statistics come from the
-    per-mixture tables (asw_shift_stack_norm_tab) instead of a pass over every patch."""
+    per-mixture tables (asw_shift_stack_norm_tab) instead of a pass over every patch.
+    ``n_total`` (1,) int32 CUDA: rows [n_base, n_base + N) of a device-built table, rows >= n_total[0] skipped."""
     if mix.dim() == 2:
         mix = mix.unsqueeze(0)
     _require_cuda(mix, "mix", torch.float32)
     _require_cuda(shifts, "shifts", torch.int32)
     B, M, T = mix.shape
-    N = shifts.shape[0]
+    if shifts.dim() != 2 or shifts.shape[1] != M:
+        raise _lib.AswError(f"shifts must be (N, {M})")
+    if N is None:
+        N = shifts.shape[0] - n_base
+    if n_base < 0 or N < 0 or n_base + N > shifts.shape[0]:
+        raise _lib.AswError(f"rows [{n_base}, {n_base + N}) exceed the shift table's {shifts.shape[0]} rows")
     if mix_index is not None:
         _require_cuda(mix_index, "mix_index", torch.int32)
+        if mix_index.shape[0] < n_base + N:
+            raise _lib.AswError("mix_index is shorter than the shift table")
+    if n_total is not None:
+        _require_cuda(n_total, "n_total", torch.int32)
     if out is None:
         out = torch.empty((N, M, T), device=mix.device, dtype=torch.float32)
     else:
@@ -502,13 +561,17 @@ def shift_stack_norm(mix, shifts, mix_index=None, out=None, tables=None, max_lag
         return out[:0], means.view(0, 1, 1), stds.view(0, 1, 1)
     mip = _ptr(mix_index) if mix_index is not None else None
     with torch.cuda.device(mix.device):     # handle-less entry points launch on the current device
-        if tables is not None:
-            _require_cuda(tables, "tables", torch.float64)
-            if tables.dim() != 2 or tables.shape[0] != B:
-                raise _lib.AswError("tables must be (B, table_len)")
-            _lib.check(_lib.load().asw_shift_stack_norm_tab(_ptr(mix), _ptr(shifts), mip, N, B, M, T, _ptr(tables),
-                                                            int(tables.shape[1]), int(max_lag), _ptr(out), _ptr(means),
-                                                            _ptr(stds), _ptr(work), _stream(mix.device)))
+        if tables is not None or n_total is not None or n_base:
+            tl = 0
+            if tables is not None:
+                _require_cuda(tables, "tables", torch.float64)
+                if tables.dim() != 2 or tables.shape[0] != B:
+                    raise _lib.AswError("tables must be (B, table_len)")
+                tl = int(tables.shape[1])
+            _lib.check(_lib.load().asw_shift_stack_norm_tab(
+                _ptr(mix), _ptr(shifts), mip, N, B, M, T, _ptr(tables) if tables is not None else None, tl, int(max_lag),
+                _ptr(out), _ptr(means), _ptr(stds), _ptr(work), _ptr(n_total) if n_total is not None else None,
+                int(n_base), _stream(mix.device)))
         else:
             _lib.check(_lib.load().asw_shift_stack_norm(_ptr(mix), _ptr(shifts), mip, N, B, M, T, _ptr(out),
                                                         _ptr(means), _ptr(stds), _ptr(work), _stream(mix.device)))

@@ -129,6 +129,49 @@ class FrontEnd:
             if consumer is not None:
                 consumer(buf, i, n)
 
+    # ---- fine stage --------------------------------------------------------------------------------
+    def upper_bound_pairwise(self):
+        """sep/Mic_Array.py:113-115: largest physical TDoA (+ 8 cm) of every mic against mic 0, in samples."""
+        mic = self.node.mic_pos
+        return (np.linalg.norm(mic[1:] - mic[:1], axis=1) + 0.08) / self.node.C * self.node.FS
+
+    def fine_table(self, n_sel, offsets, widths, capacity, max_leaves=128):
+        """Spotform_Small_Patch_Parallel's patch-list assembly (sep/Mic_Array.py:244-262) for a whole batch on the
+        device: every selected coarse patch of every mixture is a candidate, all of them are subdivided in one
+        asw_subdivide launch (search_area, local_utils_3d.py:212-335) and their leaves + centre patches become one
+        dense shift table.  ``n_sel`` (B,), ``offsets`` (B, P, D), ``widths`` (B, P) as returned by ``select``.
+        -> (shifts (capacity, M), mix_index, cand_index, cand_start (B * P + 1,), n_total (1,), status (B * P,),
+        leaf_count (B * P,)); nothing is copied to the host."""
+        B, P, D = offsets.shape
+        dev = offsets.device
+        slot = torch.arange(P, device=dev, dtype=torch.int32)
+        valid = slot[None, :] < n_sel.clamp(max=P)[:, None]
+        w = (widths * valid).reshape(-1).to(torch.int32).contiguous()          # width 0 = empty slot
+        owner = torch.arange(B, device=dev, dtype=torch.int32)[:, None].expand(B, P).reshape(-1).contiguous()
+        cnt, off, _, root, status = native.subdivide_device(self.node.native_select, offsets.reshape(-1, D).contiguous(),
+                                                            w, self.upper_bound_pairwise(), max_leaves=max_leaves)
+        return native.build_fine_table(cnt, off, root, w, owner, capacity) + (status, cnt)
+
+    def stack_norm_counted(self, mix_dev, shifts, mix_index, n_total, n_rows, tables=None, max_lag=0, consumer=None,
+                           events=None):
+        """Fused shift-stack + normalize_input of rows [0, n_rows) of a device-built table, ``net_batch`` patches per
+        launch into the ring; rows >= n_total[0] are skipped on the device.  ``tables``: CorrTables.compute(mix_dev)."""
+        B, M, T = mix_dev.shape
+        bufs = self._ring(M, T)
+        for k, i in enumerate(range(0, n_rows, self.net_batch)):
+            n = min(self.net_batch, n_rows - i)
+            buf = bufs[k % self.ring]
+            if events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            out, mu, sd = native.shift_stack_norm(mix_dev, shifts, mix_index, out=buf, tables=tables, max_lag=max_lag,
+                                                  n_total=n_total, n_base=i, N=n)
+            if events is not None:
+                e1.record()
+                events.append((e0, e1, n))
+            if consumer is not None:
+                consumer(out, mu, sd, i, n)
+
     # ---- host helpers ----------------------------------------------------------------------------
     def prune_host(self, srp_map_host):
         """The reference's pruning (SRP_Prunning.py:347-357, 500-643) on one mixture's map -> list[Patch]."""

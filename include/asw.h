@@ -201,9 +201,13 @@ int asw_corr_create(asw_corr_t** out, int device, int M, int max_lag);
 int asw_corr_destroy(asw_corr_t* h);
 int asw_corr_table_len(const asw_corr_t* h);
 int asw_corr_tables(asw_corr_t* h, const float* mix_dev, int B, int T, double* tables_dev, void* stream);
+/* tables_dev may be NULL (exact pass for every patch).  With n_valid_dev != NULL the call covers rows
+ * [n_base, n_base + N) of a device-built table (asw_build_shift_table / asw_build_fine_table) and skips the rows at
+ * or beyond *n_valid_dev, like asw_shift_stack_counted; out / means / stds / work are indexed from 0. */
 int asw_shift_stack_norm_tab(const float* mix_dev, const int32_t* shifts_dev, const int32_t* mix_index_dev,
                              int N, int B, int M, int T, const double* tables_dev, int table_len, int max_lag,
-                             float* out_dev, float* means_dev, float* stds_dev, double* work_dev, void* stream);
+                             float* out_dev, float* means_dev, float* stds_dev, double* work_dev,
+                             const int32_t* n_valid_dev, int n_base, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Peak picking on the device: fill_powermap_torch + MAX_POWER + find_valid_peak_new
@@ -284,6 +288,20 @@ int asw_subdivide(asw_select_t* h, const int32_t* centres_dev, const int32_t* wi
 /* Coordinates of the 1 cm volume (np.arange of SRP_Prunning.py:158-160: xx1 [Nx1], yy1 [Ny1], zz [Nz], host
  * arrays); needed once per handle before asw_subdivide is asked for leaf centres. */
 int asw_select_set_grid1(asw_select_t* h, const double* xx1, const double* yy1, const double* zz);
+
+/* Dense shift table of the fine stage, the patch-list assembly of Spotform_Small_Patch_Parallel
+ * (sep/Mic_Array.py:244-262) for n candidates at once, from asw_subdivide's outputs: candidate i (skipped when
+ * widths_dev[i] <= 0, the empty slots of a padded batch) contributes its min(leaf_count[i], max_leaves) leaves
+ * followed by one centre patch at root_after[i][0], its offsets after check_out (:250-256).
+ *   owner_dev      [n] int32 or NULL   mixture each candidate belongs to (-> mix_index_dev)
+ *   shifts_dev     [capacity][D+1] int32 out (column 0 = 0), mix_index_dev [capacity] int32 out
+ *   cand_index_dev [capacity] int32 out or NULL: candidate of every row
+ *   cand_start_dev [n+1] int32 out: first row of every candidate (patches_indexes of :247, :262)
+ *   n_total_dev    [1] int32 out = min(total rows, capacity) */
+int asw_build_fine_table(const int32_t* leaf_count_dev, const int32_t* leaf_off_dev, const int32_t* root_after_dev,
+                         const int32_t* widths_dev, const int32_t* owner_dev, int n, int max_leaves, int D,
+                         int32_t* shifts_dev, int32_t* mix_index_dev, int32_t* cand_index_dev, int32_t* cand_start_dev,
+                         int32_t* n_total_dev, int capacity, void* stream);
 
 /* Dense shift table for asw_shift_stack from the per-mixture patch lists above:
  *   shifts_dev [capacity][D+1] int32 (column 0 = 0), mix_index_dev [capacity] int32,

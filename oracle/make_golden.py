@@ -116,14 +116,67 @@ def shift_fixture(ns):
     print("shift: ok")
 
 
+AUDIO_DECIMATION = 97
+
+
+def pcm_content(x):
+    """16-bit PCM content carried as float32: normalize_input's re-quantisation is then the identity, so a device
+    spot model whose network is the delay-and-sum stand-in reproduces ``DelayAndSumSpot`` up to float32 rounding."""
+    return (np.clip(np.rint(x * 32768.0), -32768, 32767) / 32768.0).astype(np.float32)
+
+
+def spotform_fixture(ns, name, scene, n_spk, T, seed, max_candidates):
+    """The whole post-pruning chain of the reference with the stand-in separator: Spotform_Big_Patch ->
+    Spotform_Small_Patch_Parallel (sep/Mic_Array.py:196-395); what the latter returns is the fixture."""
+    from acousticswarms_speech_b200 import synth
+    mix = pcm_content(synth.mixture(scene, n_spk, T, seed))
+    MA = ns.Mic_Array.Mic_Array(scene.mic_positions, Spk_Range=scene.roi)
+    patches, _ = MA.Apply_SRP_PHAT(torch.tensor(mix))
+    spot = DelayAndSumSpot(ns)
+    kept = MA.Spotform_Big_Patch(torch.tensor(mix), copy.deepcopy(patches), spot)
+    cands = copy.deepcopy(kept[:max_candidates])
+    pairs = MA.Spotform_Small_Patch_Parallel(torch.tensor(mix), cands, spot)
+    D = scene.mic_positions.shape[0] - 1
+    centres = [pc.center_pos() for pc, *_ in pairs]
+    out = {
+        "mic_positions": scene.mic_positions, "roi": np.array(scene.roi), "fs": scene.fs, "n_spk": n_spk, "T": T,
+        "seed": seed, "mix_sha": sha(mix), "max_candidates": max_candidates,
+        "patch_offsets": np.array([p.sample_offset for p in patches], dtype=np.int64).reshape(len(patches), D),
+        "patch_widths": np.array([p.width_list for p in patches], dtype=np.int64).reshape(len(patches), D),
+        "kept_offsets": np.array([p.sample_offset for p in kept], dtype=np.int64).reshape(len(kept), D),
+        "relative_threshold": MA.Relative_Threshold,
+        "spotforming_times": MA.spotforming_times,
+        "cands_after_offsets": np.array([c.sample_offset for c in cands], dtype=np.int64).reshape(len(cands), D),
+        "cands_after_widths": np.array([c.width_list for c in cands], dtype=np.int64).reshape(len(cands), D),
+        "tags": np.array([t for _, _, _, t, _, _ in pairs]),
+        "powers": np.array([p for _, _, p, _, _, _ in pairs], dtype=np.float64),
+        "audio_offsets": np.array([o["audio_offset"] for *_, o, _ in pairs], dtype=np.int64).reshape(len(pairs), D),
+        "localization_offsets": np.array([o["localization_offset"] for *_, o, _ in pairs], dtype=np.float64).reshape(len(pairs), D),
+        "centres": np.array([c if c is not None else [np.nan] * 3 for c in centres], dtype=np.float64).reshape(len(pairs), 3),
+        "centre_area_sizes": np.array([pc.area_size() for pc, *_ in pairs], dtype=np.int64),
+        "centre_is_peak": np.array([pc.peak_pos is not None for pc, *_ in pairs]),
+        "labels": np.array([l for *_, l in pairs], dtype=np.int64),
+        "audio_dec": np.array([a[::AUDIO_DECIMATION] for _, a, *_ in pairs], dtype=np.float32).reshape(len(pairs), -1),
+        "audio_sha": np.array([sha(np.asarray(a, dtype=np.float32)) for _, a, *_ in pairs]),
+    }
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(f"{name}: patches={len(patches)} kept={len(kept)} candidates={len(cands)} fine={MA.spotforming_times} "
+          f"outputs={len(pairs)} tags={list(out['tags'])}")
+
+
 def main():
     from acousticswarms_speech_b200 import synth
     from oracle import ref_loader
     os.makedirs(GOLDEN, exist_ok=True)
     ns = ref_loader.load()
-    shift_fixture(ns)
-    scene_fixture(ns, "small_scene", synth.small_scene(n_mics=4, seed=2), 2, 36000, 7, store_mix=True)
-    scene_fixture(ns, "desk_scene", synth.desk_array(7, np.random.default_rng(0)), 3, 144000, 0, store_mix=False)
+    what = sys.argv[1:] or ["scenes", "spotform"]
+    if "scenes" in what:
+        shift_fixture(ns)
+        scene_fixture(ns, "small_scene", synth.small_scene(n_mics=4, seed=2), 2, 36000, 7, store_mix=True)
+        scene_fixture(ns, "desk_scene", synth.desk_array(7, np.random.default_rng(0)), 3, 144000, 0, store_mix=False)
+    if "spotform" in what:      # python -m oracle.make_golden spotform   (leaves the fixtures above untouched)
+        spotform_fixture(ns, "small_spotform", synth.small_scene(n_mics=4, seed=2), 2, 36000, 7, max_candidates=6)
+        spotform_fixture(ns, "desk_spotform", synth.desk_array(7, np.random.default_rng(0)), 3, 144000, 0, max_candidates=8)
 
 
 if __name__ == "__main__":

@@ -48,6 +48,26 @@ def decision_margin(node, gmap, max_power):
     return out
 
 
+_GEO = {}
+
+
+def oracle_geometry(scene):
+    """oracle/geometry_oracle.py's literal restatement of the table build for ``scene`` (cached: ~10 s of CPU)."""
+    from oracle import geometry_oracle
+    key = (scene.mic_positions.tobytes(), tuple(scene.roi))
+    if key not in _GEO:
+        _GEO[key] = geometry_oracle.GeometryOracle(scene.mic_positions, scene.roi)
+    return _GEO[key]
+
+
+def opatches_of(geo, m, scene):
+    m64 = np.asarray(m, dtype=np.float64)
+    pm, pi = prune_oracle.fill_powermap(m64, geo.clusters, (geo.Lx, geo.Ly, geo.Lz))
+    peaks = prune_oracle.find_valid_peaks(pm, pi, geo.dis_matrix, float(m64.max()), len(geo.clusters))
+    return prune_oracle.local_source_adaptive(m64, peaks, geo.grids, [c[0] for c in geo.clusters],
+                                              scene.mic_positions.shape[0], geo)
+
+
 @pytest.fixture(scope="module")
 def desk():
     g = np.load(os.path.join(GOLDEN, "desk_scene.npz"))
@@ -73,14 +93,19 @@ def test_apply_srp_phat_matches_reference_golden(cuda_device, desk):
     peaks = node.find_valid_peak_new()
     want = [int(i) for i in g["peaks"]]
     diff = set(peaks) ^ set(want)
-    if diff:
-        margin = decision_margin(node, ref, float(g["max_power"]))
-        assert all(margin[i] < TIE for i in diff), f"peak sets differ beyond near-ties: {sorted(diff)}"
-    else:
-        assert peaks == want
-        assert np.array_equal(np.array([p.sample_offset for p in patches]), g["patch_offsets"])
-        assert np.array_equal(np.array([p.width_list for p in patches]), g["patch_widths"])
-        assert [p.area_size() for p in patches] == list(g["patch_area_sizes"])
+    # north_star allows the index set to differ at near-ties (< 1e-5 relative); for the COMMITTED fixture the near-tie
+    # set is empty on sm_100a (the kernels are deterministic), so everything below is asserted unconditionally and a
+    # failure reports how close to a tie the offending hypercubes were
+    margin = decision_margin(node, ref, float(g["max_power"])) if diff else None
+    assert not diff, f"peak set differs from the golden one: {[(i, float(margin[i])) for i in sorted(diff)]} (near-tie bar {TIE})"
+    assert peaks == want
+    assert np.array_equal(np.array([p.sample_offset for p in patches]), g["patch_offsets"])
+    assert np.array_equal(np.array([p.width_list for p in patches]), g["patch_widths"])
+    assert [p.area_size() for p in patches] == list(g["patch_area_sizes"])
+    assert [sha(p.area_points) for p in patches] == [str(x) for x in g["patch_area_sha"]]
+    # how far the fixture is from a tie at all: the smallest relative decision margin of any hypercube
+    print(f"golden desk scene: {len(peaks)} peaks identical; smallest decision margin "
+          f"{float(decision_margin(node, ref, float(g['max_power'])).min()):.2e} (near-tie bar {TIE})")
 
 
 class MeanOverMics(torch.nn.Module):
@@ -236,9 +261,27 @@ def test_device_greedy_selection_equals_host(cuda_device, desk):
             assert np.array_equal(a.peak_pos, b.peak_pos)
     for a, b in zip(dev_lists[0][:3], host_lists[0][:3]):
         assert np.array_equal(a.area_points, b.area_points)       # built lazily by the same host routine
-    # golden: the reference's own patches for mixture 0 (when its peak set had no near-tie difference)
-    if [int(i) for i in g["peaks"]] == fe.find_peaks(smap[:1])[0][0]:
-        assert np.array_equal(np.array([p.sample_offset for p in dev_lists[0]]), g["patch_offsets"])
+    # golden: the reference's own peaks and patches for mixture 0 (no near-tie in the committed fixture, see above)
+    assert [int(i) for i in g["peaks"]] == fe.find_peaks(smap[:1])[0][0]
+    assert np.array_equal(np.array([p.sample_offset for p in dev_lists[0]]), g["patch_offsets"])
+    assert np.array_equal(np.array([p.width_list for p in dev_lists[0]]), g["patch_widths"])
+    # and the ORACLE (not the package's host mirror) on the device's own float32 maps, every mixture, C2 size:
+    # find_valid_peaks + local_source_adaptive of oracle/prune_oracle.py over the oracle's own geometry build
+    geo = oracle_geometry(scene)
+    assert np.array_equal(geo.grids, node.grids)
+    maps = smap.cpu().numpy()
+    for b in range(mixes.shape[0]):
+        m64 = maps[b].astype(np.float64)
+        pm, pi = prune_oracle.fill_powermap(m64, geo.clusters, (geo.Lx, geo.Ly, geo.Lz))
+        opeaks = prune_oracle.find_valid_peaks(pm, pi, geo.dis_matrix, float(m64.max()), len(geo.clusters))
+        opatches = prune_oracle.local_source_adaptive(m64, opeaks, geo.grids, [c[0] for c in geo.clusters],
+                                                      scene.mic_positions.shape[0], geo)
+        assert [list(p.sample_offset) for p in dev_lists[b]] == [list(p.sample_offset) for p in opatches]
+        assert [list(p.width_list) for p in dev_lists[b]] == [list(p.width_list) for p in opatches]
+        for a, o in zip(dev_lists[b], opatches):
+            assert np.array_equal(a.peak_pos, o.peak_pos)
+    for a, o in zip(dev_lists[1][:2], opatches_of(geo, maps[1], scene)[:2]):
+        assert np.array_equal(a.area_points, o.area_points)
     # device shift table -> counted shift-stack == oracle shift of every selected patch, in order
     n, off, wid, pk = fe.select(smap)
     cap = 5 * 64
@@ -287,8 +330,7 @@ def test_spotform_big_and_small_patch_drop_in(cuda_device, desk):
     from acousticswarms_speech_b200.patch import Patch
     spot = DataParallelSpotModel(MeanOverMics(), batch_size=128)
     patches, _ = ma.Apply_SRP_PHAT(torch.from_numpy(mix))
-    if not np.array_equal(np.array([p.sample_offset for p in patches]), g["patch_offsets"]):
-        pytest.skip("peak set differs from the golden one at a near-tie")
+    assert np.array_equal(np.array([p.sample_offset for p in patches]), g["patch_offsets"])   # no near-tie in the fixture
     # coarse stage
     kept = ma.Spotform_Big_Patch(torch.from_numpy(mix), copy.deepcopy(patches), spot)
     opatches = [prune_oracle.Patch(p.sample_offset.copy(), p.width_list.copy(), p.area_points, p.peak_pos) for p in patches]
@@ -484,6 +526,85 @@ def test_device_subdivision_equals_host(cuda_device, desk):
                         assert np.array_equal(a.area_points, b.area_points)
         finally:
             ma.upper_bound_pairwise = saved
+
+
+def test_device_subdivision_equals_oracle_at_c2_size(cuda_device, desk):
+    """asw_subdivide compared DIRECTLY with oracle/subdivide_oracle.py (not with the package's host mirror): every
+    coarse patch of full-size C2 mixtures, selected on the device, subdivided on the device; the oracle subdivides its
+    own patches (own geometry build, own area points).  Leaf offsets / widths / order, the per-candidate index and the
+    check_out mutation of the candidates must be identical."""
+    import copy
+    from oracle import subdivide_oracle
+    from acousticswarms_speech_b200.pipeline import FrontEnd
+    g, scene, mix, ma = desk
+    fe = FrontEnd(ma.SRP_node)
+    geo = oracle_geometry(scene)
+    mixes = np.stack([mix, synth.mixture(scene, 5, mix.shape[1], seed=51)])
+    smap = fe.score(torch.from_numpy(mixes).cuda())[0]
+    dev_lists = fe.prune(smap)
+    maps = smap.cpu().numpy()
+    n_leaves = 0
+    for b in range(mixes.shape[0]):
+        opatches = opatches_of(geo, maps[b], scene)
+        assert [list(p.sample_offset) for p in dev_lists[b]] == [list(p.sample_offset) for p in opatches]
+        cands = copy.deepcopy(dev_lists[b])
+        total, index, _, _ = ma.small_patch_list(cands)
+        ocands = copy.deepcopy(opatches)
+        ototal, oindex = subdivide_oracle.small_patch_list(ocands, scene.mic_positions)
+        assert index == oindex
+        assert [list(p.sample_offset) for p in total] == [list(p.sample_offset) for p in ototal]
+        assert [list(p.width_list) for p in total] == [list(p.width_list) for p in ototal]
+        assert [list(c.sample_offset) for c in cands] == [list(c.sample_offset) for c in ocands]
+        assert [list(c.width_list) for c in cands] == [list(c.width_list) for c in ocands]
+        for a, o in list(zip(total, ototal))[::37]:
+            ca, co = a.center_pos(), o.center_pos()
+            assert (ca is None) == (co is None) and (co is None or np.abs(ca - co).max() <= 1e-12)
+        n_leaves += len(total)
+    assert n_leaves > 1000
+
+
+class HalfMeanNet(torch.nn.Module):
+    """The network whose DataParallelSpotModel reproduces oracle/make_golden.py's DelayAndSumSpot on 16-bit PCM content:
+    (normalised mean over mics) x {1 coarse, 0.5 fine}; unnormalize restores the scale, the callers remove the mean."""
+
+    def forward(self, x, cond):
+        return x.mean(1, keepdim=True) * (cond[:, 1:2] + 0.5 * cond[:, 0:1]).unsqueeze(-1)
+
+
+@pytest.mark.parametrize("name", ["small_spotform", "desk_spotform"])
+def test_spotform_small_patch_parallel_output_matches_reference_golden(cuda_device, name):
+    """The whole drop-in chain on the device -- Apply_SRP_PHAT -> Spotform_Big_Patch -> Spotform_Small_Patch_Parallel
+    (sep/Mic_Array.py:152-395) -- against what the UNMODIFIED reference returned for the same mixture with the
+    delay-and-sum stand-in separator (tests/golden/*_spotform.npz, oracle/make_golden.py): kept candidates, their
+    check_out mutation, and for every output its tag (candidate _ cluster head: the power gates and the SI-SDR
+    grouping), separation / localisation offsets (weight_mean_pos), merged centre (find_merge_center), power, audio."""
+    import copy
+    from _golden_checks import check_spotform_pairs, pcm_content
+    from acousticswarms_speech_b200.mic_array import Mic_Array
+    from acousticswarms_speech_b200.spot import DataParallelSpotModel
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    scene = synth.Scene(g["mic_positions"], list(g["roi"]), int(g["fs"]))
+    mix = pcm_content(synth.mixture(scene, int(g["n_spk"]), int(g["T"]), int(g["seed"])))
+    if sha(mix) != str(g["mix_sha"]):
+        pytest.skip("synthetic generator stream differs from the fixture's")
+    ma = Mic_Array(scene.mic_positions, Spk_Range=scene.roi)
+    spot = DataParallelSpotModel(HalfMeanNet(), batch_size=128)
+    x = torch.from_numpy(mix)
+    patches, _ = ma.Apply_SRP_PHAT(x)
+    D = scene.mic_positions.shape[0] - 1
+    assert np.array_equal(np.array([p.sample_offset for p in patches]).reshape(-1, D), g["patch_offsets"])
+    assert np.array_equal(np.array([p.width_list for p in patches]).reshape(-1, D), g["patch_widths"])
+    kept = ma.Spotform_Big_Patch(x, copy.deepcopy(patches), spot)
+    assert np.array_equal(np.array([p.sample_offset for p in kept]).reshape(-1, D), g["kept_offsets"])
+    assert abs(ma.Relative_Threshold - float(g["relative_threshold"])) < 1e-12
+    cands = copy.deepcopy(kept[:int(g["max_candidates"])])
+    pairs = ma.Spotform_Small_Patch_Parallel(x, cands, spot)
+    assert ma.spotforming_times == int(g["spotforming_times"])
+    assert np.array_equal(np.array([c.sample_offset for c in cands]).reshape(-1, D), g["cands_after_offsets"])
+    assert np.array_equal(np.array([c.width_list for c in cands]).reshape(-1, D), g["cands_after_widths"])
+    # float32 device arithmetic vs the reference's float32 numpy: powers / audio to 1e-5 relative; the localisation
+    # offsets are power-weighted means of integer offsets a few samples apart, so 1e-5 on the weights is <= 2e-4 samples
+    check_spotform_pairs(pairs, g, power_rtol=1e-5, offset_atol=2e-4, centre_atol=1e-9)
 
 
 @pytest.mark.parametrize("n_spk,seed,noise", [(5, 101, 1e-3), (8, 102, 1e-2), (0, 103, 1e-3)])

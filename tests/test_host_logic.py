@@ -189,3 +189,26 @@ def test_window_constants():
     assert constants.window_length(144000) == 36000 and constants.window_length(60000) == 24000
     assert constants.frames_per_window(36000) == 67 and constants.frames_per_window(24000) == 43
     assert constants.window_starts(144000, 36000) == srp_oracle.window_starts(144000, 36000)
+
+
+def test_fine_stage_tdoa_rows_follow_the_array_rate():
+    """The fine stage works in the rate the hypercube table was built for (Mic_Array.fs), not in the reference's
+    constant 48 kHz: at 44.1 kHz the point TDoAs used by search_area / the leaf builders / find_merge_center must be
+    the node's own Offset_1 volume, and the 48 kHz default must stay what the reference computes."""
+    from acousticswarms_speech_b200.mic_array import find_merge_center
+    scene = synth.small_scene(n_mics=4, seed=2)
+    for fs in (44100, 48000):
+        node = host_node(scene.mic_positions, scene.roi, fs=fs)
+        pos1, off1 = node.Pos_1.reshape(-1, 3), node.Offset_1.reshape(-1, 3)
+        pick = np.random.default_rng(fs).choice(pos1.shape[0], 500, replace=False)
+        rows = local_utils._tdoa_rows(pos1[pick].T, scene.mic_positions, fs)
+        assert np.array_equal(rows.T, off1[pick])
+        if fs == 48000:
+            assert np.array_equal(local_utils._tdoa_rows(pos1[pick].T, scene.mic_positions), rows)
+            assert np.array_equal(subdivide_oracle.point_tdoas(pos1[pick].T, scene.mic_positions), rows)
+        # a merged centre taken from real voxels of that rate is found again inside its own area
+        centre = off1[pick[:40]].mean(0)
+        area = pos1[pick].T
+        pc = find_merge_center(np.round(off1[pick[0]]), area, scene.mic_positions, np.zeros(3), fs)
+        inside = np.all(np.abs(off1[pick] - np.round(off1[pick[0]])) <= 1.5 + 1e-3, axis=1)
+        assert pc.area_points is not None and pc.area_points.shape[1] == int(inside.sum()) >= 1
