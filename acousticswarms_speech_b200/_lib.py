@@ -27,6 +27,10 @@ class AswError(RuntimeError):
     pass
 
 
+class AswCapacityError(AswError):
+    """A device list was too short for the result (the call can be repeated with a larger capacity)."""
+
+
 _lib = None
 
 

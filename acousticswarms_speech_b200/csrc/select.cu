@@ -40,9 +40,15 @@ struct asw_select {
     double* d_off1 = nullptr;     // [Ny1][Nx1][Nz][D]
     double* d_grid1 = nullptr;    // [Nx1 + Ny1 + Nz] coordinates of the 1 cm volume (asw_select_set_grid1), optional
     unsigned char* d_box = nullptr;  // [G] is the untrimmed box of cluster g non-empty
+    float* d_cell = nullptr;      // [ncy][ncx][Nz][D][2] min / max of Offset_1 over each 5 x 5 x 1 block of 1 cm voxels
+    int ncx = 0, ncy = 0;
     // subdivision workspace (grown on demand): per candidate one area list and two ping-pong node lists
     int32_t* d_lists = nullptr;
     size_t lists_cap = 0;
+    int32_t* d_nodes_i = nullptr;   // node records of the level walk (see subdivide_kernel)
+    size_t nodes_i_cap = 0;
+    double* d_nodes_d = nullptr;
+    size_t nodes_d_cap = 0;
 };
 
 namespace asw {
@@ -72,6 +78,8 @@ struct SelectParams {
     const double* off1;
     int Ny1, Nx1, Nz;
     const unsigned char* box_table;   // [G] untrimmed box non-empty (null while it is being built)
+    const float* cell;                // per-cell bounds of Offset_1 (see cell_bounds_kernel), ncy x ncx x Nz cells
+    int ncx, ncy;
     int32_t* out_count;     // [B]
     int32_t* out_off;       // [B][max_patches][D]
     int32_t* out_width;     // [B][max_patches]
@@ -230,6 +238,38 @@ __device__ int area_nonempty(const SelectParams& p, const double* s_lo, const do
     return f->hit1;                                           // 0: empty init_area (:633-636)
 }
 
+// Outward-rounded min / max of every TDoA coordinate over each 5 x 5 x 1 block of the 1 cm volume.  The member scan of
+// asw_subdivide tests a block's 12 bounds before touching its 25 voxels: a coarse patch's cut (the axis-aligned bounding
+// box of a slanted hyperbolic sliver, up to ~1e6 voxels) is mostly voxels far outside the TDoA box.  Exact by
+// construction: a block is skipped only if no voxel of it can pass the test.
+constexpr int kCell = 5;
+__global__ void __launch_bounds__(128) cell_bounds_kernel(const double* __restrict__ off1, int Ny1, int Nx1, int Nz, int D,
+                                                          int ncy, int ncx, float* __restrict__ out) {
+    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= (long long)ncy * ncx * Nz) return;
+    const int iz = (int)(cell % Nz);
+    const int cx = (int)((cell / Nz) % ncx), cy = (int)(cell / ((long long)Nz * ncx));
+    for (int i = 0; i < D; ++i) {
+        double mn = CUDART_INF, mx = -CUDART_INF;
+        bool bad = false;
+        for (int dy = 0; dy < kCell; ++dy)
+            for (int dx = 0; dx < kCell; ++dx) {
+                const int iy = kCell * cy + dy, ix = kCell * cx + dx;
+                if (iy >= Ny1 || ix >= Nx1) continue;
+                const double v = off1[(((size_t)iy * Nx1 + ix) * Nz + iz) * D + i];
+                if (!(v == v)) bad = true;
+                mn = fmin(mn, v);
+                mx = fmax(mx, v);
+            }
+        if (bad) {                                    // a NaN inside: never skip the block
+            mn = -CUDART_INF;
+            mx = CUDART_INF;
+        }
+        out[((size_t)cell * D + i) * 2] = __double2float_rd(mn);
+        out[((size_t)cell * D + i) * 2 + 1] = __double2float_ru(mx);
+    }
+}
+
 // Per-cluster table for the common untrimmed case (cut == W, so the new centre is the cluster's own TDoA
 // vector): is the box centre +- (W + 0.2)/2 non-empty?  A static property of the geometry, computed once at
 // handle creation with the same code the per-mixture kernel uses for trimmed boxes.
@@ -383,23 +423,47 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(SelectParams p) {
 // Offset_1 at the member voxels (numpy's x ** 0.5 is sqrt), so the device works on voxel indices into Offset_1.
 // A node's member set is always "root members inside an axis-aligned box" (the intersection of the closed
 // half-boxes on the path), which is also what the host needs to rebuild a leaf's area_points on demand.
-constexpr int kSubD = 8;            // TDoA dimensions supported on the device path (M <= 9)
-constexpr int kSubThreads = 256;
-constexpr int kMaxNodes = 128;      // nodes per level
+// The kernel is instantiated for three dimension buckets, KD = 8 / 16 / 32 (D <= 31 = what select_kernel supports).
+//
+// Work layout (round 2): the tree is walked level by level, and WITHIN a level every phase is parallel over what it
+// touches -- node decisions over the nodes (one thread each), member tests over the flattened member lists of all
+// nodes of the level (the lists of a level are contiguous, in node order).  The first version processed the nodes of a
+// level one after the other with ~5 block barriers and a single-thread section each: a median candidate (3 k member
+// voxels, ~45 nodes) took 1.2 ms of almost pure barrier latency, the largest (39 k) 5 ms, and a batch of 542
+// candidates 5-7 ms whatever the occupancy.  Now a level costs 5 barriers in total.
+// Node records live in global scratch (read through L1; two buffers per candidate, ping-pong by level); shared memory
+// holds only the per-node counters.  Slot assignment (leaf numbers, child slots, list offsets) is one short serial
+// pass per level, which is what keeps the reference's order: leaves in level order, within a level in node order,
+// children as (lower half, upper half).
 constexpr int kListCap = 1 << 17;   // member voxels per candidate (and per level, duplicates included)
 
-struct SubNode {
-    int c[kSubD], w[kSubD];
-    double lo[kSubD], hi[kSubD];    // membership box relative to the root's members
-    int start, count;
+template <int KD>
+struct SubCfg {
+    static constexpr int kNodes = KD <= 8 ? 128 : (KD <= 16 ? 256 : 384);   // nodes per level
+    static constexpr int kNI = 2 * KD + 8;                                   // ints per node record
+    static constexpr int kND = 8 * KD;                                       // doubles per node record
+    // One candidate per SM with as many warps as the register file allows: a candidate's time is what its own warps
+    // can issue (2 warps per scheduler, mostly waiting on dependent loads, gave IPC 0.25 and a 4 ms tail for the
+    // candidates with ~4e4 member voxels whatever else ran on the GPU), so threads per CANDIDATE matter, not CTAs per SM.
+    static constexpr int kThreads = KD <= 8 ? 1024 : 512;
+    static constexpr int kCtasPerSm = 1;
+    static constexpr size_t smem_bytes() {
+        return sizeof(double) * kNodes * 3 + sizeof(int) * ((size_t)kNodes * KD * 2 + kNodes * 2 + 2 * (kNodes + 1));
+    }
 };
+// int fields after c[KD], w[KD]
+enum { kFStart = 0, kFCount, kFFlag, kFChosen, kFSize0, kFSize1, kFSlot, kFOff0 };
+enum { kNodeSplit = 0, kNodeLeaf = 1, kNodeDropped = 2 };
 
 struct SubParams {
     SelectParams g;                 // geometry
     const int32_t* centres;         // [n][D]
-    const int32_t* widths;          // [n] coarse width (identical in every dimension)
-    double ub[kSubD];               // upper_bound_pairwise (sep/Mic_Array.py:113-115)
+    const int32_t* widths;          // [n] coarse width (identical in every dimension); <= 0: empty slot
+    double ub[kMaxD];               // upper_bound_pairwise (sep/Mic_Array.py:113-115)
     int32_t* lists;                 // [n][3][kListCap]: area list, ping, pong
+    int32_t* nodes_i;               // [n][2][kNodes][kNI]
+    double* nodes_d;                // [n][2][kNodes][kND]: lo[KD], hi[KD] (membership box relative to the root's members),
+                                    // then [KD][6] the bounds of the member tests (DimBounds), written once per node
     int max_leaves;
     int32_t* leaf_count;            // [n]
     int32_t* leaf_off;              // [n][max_leaves][D]
@@ -417,21 +481,50 @@ struct SubParams {
 
 __device__ __forceinline__ long long trunc_ll(double x) { return (long long)x; }   // numpy float -> int64 item assignment
 
-__global__ void __launch_bounds__(kSubThreads) subdivide_kernel(SubParams q) {
+// The bounds every membership test of a node is made of (all double, evaluated exactly as the first version did):
+//   node box   c -+ w/2 -+ 1e-3                      Patch.hyperbola_sample (Patch_3D.py:40-47) on the checked-out node
+//   half boxes hc -+ hw/2 -+ 1e-3, hc = trunc(c -+ w/4), hw = trunc(w/2)    binary_area_divide_width (:275-281)
+struct DimBounds {
+    double blo, bhi, hlo0, hhi0, hlo1, hhi1;
+    int hw, hc0, hc1, elig;
+};
+__device__ __forceinline__ DimBounds dim_bounds(int ci, int wi) {
+    DimBounds b;
+    const double c = (double)ci, w = (double)wi;
+    b.blo = c - w / 2.0 - 1e-3;
+    b.bhi = c + w / 2.0 + 1e-3;
+    b.elig = (w / 2.0 < 3.0) ? 0 : 1;                 // (:271-272) MIN_WIDTH
+    b.hw = (int)trunc_ll(w / 2.0);                    // (:279-280) float into int64
+    b.hc0 = (int)trunc_ll(c - w / 4.0);               // (:275-278)
+    b.hc1 = (int)trunc_ll(c + w / 4.0);
+    b.hlo0 = (double)b.hc0 - (double)b.hw / 2.0 - 1e-3;
+    b.hhi0 = (double)b.hc0 + (double)b.hw / 2.0 + 1e-3;
+    b.hlo1 = (double)b.hc1 - (double)b.hw / 2.0 - 1e-3;
+    b.hhi1 = (double)b.hc1 + (double)b.hw / 2.0 + 1e-3;
+    return b;
+}
+
+template <int KD>
+__global__ void __launch_bounds__(SubCfg<KD>::kThreads, SubCfg<KD>::kCtasPerSm) subdivide_kernel(SubParams q) {
+    using C = SubCfg<KD>;
+    constexpr int NN = C::kNodes, NI = C::kNI, ND = C::kND;
+    constexpr int kSubThreads = C::kThreads;
+    constexpr int kU = 4;                                                // members per thread in flight
     extern __shared__ __align__(16) unsigned char s_raw[];
-    SubNode* cur = reinterpret_cast<SubNode*>(s_raw);
-    SubNode* nxt = cur + kMaxNodes;
+    double* s_lsum = reinterpret_cast<double*>(s_raw);                   // [NN][3] leaf position sums
+    int* s_cnt = reinterpret_cast<int*>(s_lsum + NN * 3);                // [NN][KD][2]
+    int* s_pos = s_cnt + NN * KD * 2;                                    // [NN][2] append cursors of the two children
+    int* s_start = s_pos + NN * 2;                                       // [2][NN + 1] list boundaries, by level parity
     __shared__ double s_lo[kMaxD], s_hi[kMaxD];
     __shared__ ProbeShared ps;
-    __shared__ int s_n, s_cnt[kSubD][2], s_pos[2], s_flag[4];
-    __shared__ double s_blo[kSubD], s_bhi[kSubD], s_hlo[kSubD][2], s_hhi[kSubD][2];
-    __shared__ int s_elig[kSubD], s_hc[kSubD][2], s_hw[kSubD];
-    __shared__ double s_sum[kSubThreads / 32][3];
+    __shared__ int s_n, s_nc, s_state[4];                                // n_leaf, status, n_nxt, (unused)
     const SelectParams& p = q.g;
     const int tid = threadIdx.x, lane = tid & 31;
     const int cand = blockIdx.x, D = p.D;
     int32_t* area = q.lists + (size_t)cand * 3 * kListCap;
     int32_t* buf[2] = {area + kListCap, area + 2 * kListCap};
+    int32_t* nodes_i = q.nodes_i + (size_t)cand * 2 * NN * NI;
+    double* nodes_d = q.nodes_d + (size_t)cand * 2 * NN * ND;
     const int wc = q.widths[cand];
     if (wc <= 0) {                    // empty slot of a padded candidate list (batched callers): nothing to subdivide
         if (tid == 0) {
@@ -452,32 +545,75 @@ __global__ void __launch_bounds__(kSubThreads) subdivide_kernel(SubParams q) {
     if (tid == 0) s_n = 0;
     __syncthreads();
     probe5cm(p, s_lo, s_hi, &ps);
-    int status = 0;
+    int status0 = 0;
     if (ps.f.cnt5 > 0) {
         if (tid == 0) cut_box(p, &ps);
         __syncthreads();
         const int ix0 = ps.cutbox[0], nx = ps.cutbox[1] - ix0, iy0 = ps.cutbox[2], ny = ps.cutbox[3] - iy0;
-        const long long total = (nx > 0 && ny > 0) ? (long long)nx * ny * p.Nz : 0;
-        for (long long k0 = 0; k0 < total; k0 += kSubThreads) {
-            const long long k = k0 + tid;
-            bool in = false;
-            int vox = 0;
-            if (k < total) {
-                const int iz = (int)(k % p.Nz);
-                const long long r2 = k / p.Nz;
-                const int ix = ix0 + (int)(r2 % nx), iy = iy0 + (int)(r2 / nx);
-                vox = (iy * p.Nx1 + ix) * p.Nz + iz;
-                const double* o = p.off1 + (size_t)vox * D;
-                in = true;
-                for (int i = 0; i < D; ++i) in = in && (o[i] >= s_lo[i]) && (o[i] <= s_hi[i]);
+        // Stage 1: the 5 x 5 x 1 blocks overlapping the cut whose offset bounds intersect the TDoA box (see
+        // cell_bounds_kernel), compacted into the (still unused) ping list as packed (ix, iy, iz) of the block's corner.
+        int32_t* cells = buf[0];
+        if (tid == 0) s_nc = 0;
+        __syncthreads();
+        if (nx > 0 && ny > 0) {
+            const int cx0 = ix0 / kCell, cx1 = (ix0 + nx - 1) / kCell, cy0 = iy0 / kCell, cy1 = (iy0 + ny - 1) / kCell;
+            const int ncx = cx1 - cx0 + 1, rowc = ncx * p.Nz;              // one row of blocks: cx, iz
+            for (int cy = cy0; cy <= cy1; ++cy)
+                for (int j0 = 0; j0 < rowc; j0 += kSubThreads) {
+                    const int j = j0 + tid;
+                    bool hit = j < rowc;
+                    int cx = 0, iz = 0;
+                    if (hit) {
+                        cx = cx0 + j / p.Nz;
+                        iz = j - (j / p.Nz) * p.Nz;
+                        const float* cb = p.cell + (((size_t)cy * p.ncx + cx) * p.Nz + iz) * D * 2;
+                        for (int i = 0; i < D; ++i)
+                            hit = hit && ((double)cb[2 * i + 1] >= s_lo[i]) && ((double)cb[2 * i] <= s_hi[i]);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    int base = 0;
+                    if (lane == 0 && m) base = atomicAdd(&s_nc, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (hit) {
+                        const int pos = base + __popc(m & ((1u << lane) - 1));
+                        if (pos < kListCap) cells[pos] = (kCell * cx) | ((kCell * cy) << 12) | (iz << 24);
+                    }
+                }
+        }
+        __syncthreads();
+        // Stage 2: the voxels of those blocks that lie inside the cut, tested exactly as the reference does
+        const int ncell = min(s_nc, kListCap);
+        if (s_nc > kListCap) status0 = 1;
+        for (int j0 = 0; j0 < ncell * (kCell * kCell); j0 += 2 * kSubThreads) {
+            bool in[2];
+            int vox[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int j = j0 + u * kSubThreads + tid;
+                in[u] = j < ncell * (kCell * kCell);
+                vox[u] = 0;
+                if (in[u]) {
+                    const int c = cells[j / (kCell * kCell)], l = j % (kCell * kCell);
+                    const int ix = (c & 0xfff) + l % kCell, iy = ((c >> 12) & 0xfff) + l / kCell, iz = (c >> 24) & 0xff;
+                    in[u] = ix >= ix0 && ix < ix0 + nx && iy >= iy0 && iy < iy0 + ny;
+                    if (in[u]) vox[u] = (iy * p.Nx1 + ix) * p.Nz + iz;
+                }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, in);
-            int base = 0;
-            if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (in) {
-                const int pos = base + __popc(m & ((1u << lane) - 1));
-                if (pos < kListCap) area[pos] = vox;
+            for (int i = 0; i < D; ++i) {
+                const double v0 = p.off1[(size_t)vox[0] * D + i], v1 = p.off1[(size_t)vox[1] * D + i];
+                in[0] = in[0] && (v0 >= s_lo[i]) && (v0 <= s_hi[i]);
+                in[1] = in[1] && (v1 >= s_lo[i]) && (v1 <= s_hi[i]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const unsigned m = __ballot_sync(0xffffffffu, in[u]);
+                int base = 0;
+                if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (in[u]) {
+                    const int pos = base + __popc(m & ((1u << lane) - 1));
+                    if (pos < kListCap) area[pos] = vox[u];
+                }
             }
         }
     }
@@ -485,7 +621,7 @@ __global__ void __launch_bounds__(kSubThreads) subdivide_kernel(SubParams q) {
     int n_root = s_n;
     if (n_root > kListCap) {
         n_root = kListCap;
-        status = 1;
+        status0 = 1;
     }
 
     if (q.root_members) {             // Patch.area_points of the candidate, as voxel indices (the host sorts them)
@@ -495,260 +631,397 @@ __global__ void __launch_bounds__(kSubThreads) subdivide_kernel(SubParams q) {
     }
 
     // ---- level-synchronous walk of the split tree
-    int n_cur = 1, n_leaf = 0;
     if (tid == 0) {
+        int32_t* r = nodes_i;
+        double* rd = nodes_d;
         for (int i = 0; i < D; ++i) {
-            cur[0].c[i] = q.centres[(size_t)cand * D + i];
-            cur[0].w[i] = wc;
-            cur[0].lo[i] = s_lo[i];
-            cur[0].hi[i] = s_hi[i];
+            r[i] = q.centres[(size_t)cand * D + i];
+            r[KD + i] = wc;
+            rd[i] = s_lo[i];
+            rd[KD + i] = s_hi[i];
         }
-        cur[0].start = 0;
-        cur[0].count = n_root;
+        r[2 * KD + kFStart] = 0;
+        r[2 * KD + kFCount] = n_root;
+        s_start[0] = 0;
+        s_start[1] = n_root;
+        s_state[0] = 0;
+        s_state[1] = status0;
+        s_state[2] = 0;
     }
     __syncthreads();
     const int32_t* src = area;
-    int level = 0;
+    int n_cur = 1, level = 0;
+    const unsigned all = (D >= 32) ? 0xffffffffu : ((1u << D) - 1);
     while (n_cur > 0) {
         int32_t* dst = buf[level & 1];
-        int n_nxt = 0, dst_off = 0;
-        for (int ni = 0; ni < n_cur; ++ni) {
-            SubNode* nd = &cur[ni];
-            if (tid == 0) {
-                // Patch.check_out (Patch_3D.py:69-87), in place
-                for (int i = 0; i < D; ++i) {
-                    while (true) {
-                        const int c = nd->c[i], w = nd->w[i];
-                        if (fabs((double)c) <= q.ub[i] || w <= 4) break;
-                        if ((double)c > q.ub[i]) nd->c[i] = (int)trunc_ll((double)c - (double)w / 4.0);
-                        else if ((double)c < -q.ub[i]) nd->c[i] = (int)trunc_ll((double)c + (double)w / 4.0);
-                        nd->w[i] = (int)trunc_ll((double)w / 2.0);
-                    }
+        int32_t* ni = nodes_i + (size_t)(level & 1) * NN * NI;
+        double* nd = nodes_d + (size_t)(level & 1) * NN * ND;
+        int32_t* ni_nxt = nodes_i + (size_t)((level + 1) & 1) * NN * NI;
+        double* nd_nxt = nodes_d + (size_t)((level + 1) & 1) * NN * ND;
+        const int* start = s_start + (level & 1) * (NN + 1);
+        int* start_nxt = s_start + ((level + 1) & 1) * (NN + 1);
+        const int total = start[n_cur];
+
+        // ---- A1, one thread per node: Patch.check_out (Patch_3D.py:69-87) in place, the leaf test of :260-262
+        for (int node = tid; node < n_cur; node += kSubThreads) {
+            int32_t* r = ni + (size_t)node * NI;
+            int wmax = 0;
+            for (int i = 0; i < D; ++i) {
+                int c = r[i], w = r[KD + i];
+                while (true) {
+                    if (fabs((double)c) <= q.ub[i] || w <= 4) break;
+                    if ((double)c > q.ub[i]) c = (int)trunc_ll((double)c - (double)w / 4.0);
+                    else if ((double)c < -q.ub[i]) c = (int)trunc_ll((double)c + (double)w / 4.0);
+                    w = (int)trunc_ll((double)w / 2.0);
                 }
-                if (level == 0)
-                    for (int i = 0; i < D; ++i) {
-                        q.root_after[((size_t)cand * 2 + 0) * D + i] = nd->c[i];
-                        q.root_after[((size_t)cand * 2 + 1) * D + i] = nd->w[i];
-                    }
-                int wmax = 0;
-                for (int i = 0; i < D; ++i) wmax = max(wmax, nd->w[i]);
-                // (:260-262) leaf: every dimension fine enough and few enough member points
-                s_flag[0] = ((double)wmax / 2.0 <= 2.0 && nd->count <= 400) ? 1 : 0;
-                for (int i = 0; i < D; ++i) {
-                    const double c = (double)nd->c[i], w = (double)nd->w[i];
-                    s_blo[i] = c - w / 2.0 - 1e-3;            // Patch.hyperbola_sample bounds (Patch_3D.py:40-47)
-                    s_bhi[i] = c + w / 2.0 + 1e-3;
-                    s_elig[i] = (w / 2.0 < 3.0) ? 0 : 1;      // (:271-272) MIN_WIDTH
-                    const int hw = (int)trunc_ll(w / 2.0);    // (:279-280) float into int64
-                    s_hw[i] = hw;
-                    s_hc[i][0] = (int)trunc_ll(c - w / 4.0);  // (:275-278)
-                    s_hc[i][1] = (int)trunc_ll(c + w / 4.0);
-                    for (int sd = 0; sd < 2; ++sd) {
-                        s_hlo[i][sd] = (double)s_hc[i][sd] - (double)hw / 2.0 - 1e-3;
-                        s_hhi[i][sd] = (double)s_hc[i][sd] + (double)hw / 2.0 + 1e-3;
-                    }
-                    s_cnt[i][0] = 0;
-                    s_cnt[i][1] = 0;
+                r[i] = c;
+                r[KD + i] = w;
+                wmax = max(wmax, w);
+                {   // the member loops read these instead of recomputing them per member (int -> double conversions and
+                    // ten fp64 operations per dimension were a fifth of a large candidate's instructions)
+                    const DimBounds b = dim_bounds(c, w);
+                    double* bd = nd + (size_t)node * ND + 2 * KD + 6 * i;
+                    bd[0] = b.blo;
+                    bd[1] = b.bhi;
+                    bd[2] = b.hlo0;
+                    bd[3] = b.hhi0;
+                    bd[4] = b.hlo1;
+                    bd[5] = b.hhi1;
                 }
+                if (level == 0) {
+                    q.root_after[((size_t)cand * 2 + 0) * D + i] = c;
+                    q.root_after[((size_t)cand * 2 + 1) * D + i] = w;
+                }
+                s_cnt[(node * KD + i) * 2] = 0;
+                s_cnt[(node * KD + i) * 2 + 1] = 0;
             }
-            __syncthreads();
-            bool leaf = s_flag[0] != 0;
-            int chosen = -1;
-            if (!leaf) {
-                // one pass: member counts of both halves along every eligible dimension
-                int cnt[kSubD][2];
-#pragma unroll
-                for (int i = 0; i < kSubD; ++i) cnt[i][0] = cnt[i][1] = 0;
-                for (int k = tid; k < nd->count; k += kSubThreads) {
-                    const double* o = p.off1 + (size_t)src[nd->start + k] * D;
-                    unsigned in = 0;
-                    double v[kSubD];
-#pragma unroll
-                    for (int i = 0; i < kSubD; ++i)
-                        if (i < D) {
-                            v[i] = o[i];
-                            if (v[i] >= s_blo[i] && v[i] <= s_bhi[i]) in |= 1u << i;
-                        }
-                    const unsigned all = (1u << D) - 1;
-#pragma unroll
-                    for (int i = 0; i < kSubD; ++i)
-                        if (i < D && s_elig[i] && ((in | (1u << i)) == all)) {
-                            if (v[i] >= s_hlo[i][0] && v[i] <= s_hhi[i][0]) ++cnt[i][0];
-                            if (v[i] >= s_hlo[i][1] && v[i] <= s_hhi[i][1]) ++cnt[i][1];
-                        }
-                }
-#pragma unroll
-                for (int i = 0; i < kSubD; ++i)
-                    if (i < D) {
-#pragma unroll
-                        for (int sd = 0; sd < 2; ++sd) {
-                            int c = cnt[i][sd];
-#pragma unroll
-                            for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-                            if (lane == 0 && c) atomicAdd(&s_cnt[i][sd], c);
-                        }
-                    }
-                __syncthreads();
-                if (tid == 0) {
-                    // the reference's choice (:264-331): most balanced split, dimensions still wider than 2 first
-                    int best = -1, best_diff = 2500000, last = -1;
-                    bool keep8 = false;
-                    for (int i = 0; i < D; ++i) {
-                        if (!s_elig[i]) continue;
-                        last = i;
-                        const int diff = abs(s_cnt[i][0] - s_cnt[i][1]);
-                        if (s_hw[i] > 2) {
-                            if (!keep8) {
-                                best_diff = diff;
-                                best = i;
-                                keep8 = true;
-                            } else if (diff < best_diff) {
-                                best_diff = diff;
-                                best = i;
-                            }
-                        } else if (!keep8 && diff < best_diff) {
-                            best_diff = diff;
-                            best = i;
-                        }
-                    }
-                    // (:333-335) "min_patch is None or len(two_patches) == 0" -- two_patches of the LAST dimension tried
-                    if (best < 0 || last < 0 || (s_cnt[last][0] == 0 && s_cnt[last][1] == 0)) s_flag[1] = -1;
-                    else s_flag[1] = best;
-                    s_pos[0] = 0;
-                    s_pos[1] = 0;
-                }
-                __syncthreads();
-                chosen = s_flag[1];
-                if (chosen < 0) leaf = true;
-            }
-            if (leaf) {
-                if (q.leaf_centre && n_leaf < q.max_leaves) {
-                    // Patch.center_pos() of the leaf: mean of its member voxels' positions (Patch_3D.py, np.mean of
-                    // area_points); summed per thread, per warp, then over the warps in a fixed order
-                    double sx = 0.0, sy = 0.0, sz = 0.0;
-                    for (int k = tid; k < nd->count; k += kSubThreads) {
-                        const int vox = src[nd->start + k];
-                        const int iz = vox % p.Nz, r2 = vox / p.Nz;
-                        const int ix = r2 % p.Nx1, iy = r2 / p.Nx1;
-                        sx += q.grid1[ix];
-                        sy += q.grid1[p.Nx1 + iy];
-                        sz += q.grid1[p.Nx1 + p.Ny1 + iz];
-                    }
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) {
-                        sx += __shfl_xor_sync(0xffffffffu, sx, d);
-                        sy += __shfl_xor_sync(0xffffffffu, sy, d);
-                        sz += __shfl_xor_sync(0xffffffffu, sz, d);
-                    }
-                    if (lane == 0) {
-                        s_sum[tid >> 5][0] = sx;
-                        s_sum[tid >> 5][1] = sy;
-                        s_sum[tid >> 5][2] = sz;
-                    }
-                    __syncthreads();
-                    if (tid < 3) {
-                        double t = 0.0;
-                        for (int w = 0; w < kSubThreads / 32; ++w) t += s_sum[w][tid];
-                        q.leaf_centre[((size_t)cand * q.max_leaves + n_leaf) * 3 + tid] =
-                            nd->count > 0 ? t / (double)nd->count : nan("");
-                    }
-                }
-                if (tid == 0) {
-                    if (n_leaf < q.max_leaves) {
-                        const size_t lb = (size_t)cand * q.max_leaves + n_leaf;
-                        for (int i = 0; i < D; ++i) {
-                            q.leaf_off[lb * D + i] = nd->c[i];
-                            q.leaf_w[lb * D + i] = nd->w[i];
-                            q.leaf_box[(lb * 2 + 0) * D + i] = nd->lo[i];
-                            q.leaf_box[(lb * 2 + 1) * D + i] = nd->hi[i];
-                        }
-                        q.leaf_npts[lb] = nd->count;
-                    }
-                }
-                if (n_leaf >= q.max_leaves) status = 3;
-                ++n_leaf;
-                __syncthreads();
-                continue;
-            }
-            // split along `chosen`: children = the non-empty halves, in order; their members by a second pass
-            const int size0 = s_cnt[chosen][0], size1 = s_cnt[chosen][1];
-            const int off0 = dst_off, off1 = dst_off + size0;
-            const int add = (size0 > 0 ? 1 : 0) + (size1 > 0 ? 1 : 0);
-            if (off1 + size1 > kListCap) {
-                status = 1;                                   // uniform: all of these are shared values
-            } else if (n_nxt + add > kMaxNodes) {
-                status = 2;
-            } else {
-                for (int k0 = 0; k0 < nd->count; k0 += kSubThreads) {
-                    const int k = k0 + tid;
-                    bool in0 = false, in1 = false;
-                    int vox = 0;
-                    if (k < nd->count) {
-                        vox = src[nd->start + k];
-                        const double* o = p.off1 + (size_t)vox * D;
-                        bool others = true;
-                        double vi = 0.0;
-                        for (int i = 0; i < D; ++i) {
-                            const double v = o[i];
-                            if (i == chosen) vi = v;
-                            else others = others && (v >= s_blo[i]) && (v <= s_bhi[i]);
-                        }
-                        in0 = others && vi >= s_hlo[chosen][0] && vi <= s_hhi[chosen][0];
-                        in1 = others && vi >= s_hlo[chosen][1] && vi <= s_hhi[chosen][1];
-                    }
-                    // warp-aggregated append (a member within 1e-3 of the split plane goes to both halves)
-                    const unsigned m0 = __ballot_sync(0xffffffffu, in0), m1 = __ballot_sync(0xffffffffu, in1);
-                    int b0 = 0, b1 = 0;
-                    if (lane == 0) {
-                        if (m0) b0 = atomicAdd(&s_pos[0], __popc(m0));
-                        if (m1) b1 = atomicAdd(&s_pos[1], __popc(m1));
-                    }
-                    b0 = __shfl_sync(0xffffffffu, b0, 0);
-                    b1 = __shfl_sync(0xffffffffu, b1, 0);
-                    const unsigned below = (1u << lane) - 1;
-                    if (in0) dst[off0 + b0 + __popc(m0 & below)] = vox;
-                    if (in1) dst[off1 + b1 + __popc(m1 & below)] = vox;
-                }
-                if (tid == 0) {
-                    int slot = n_nxt;
-                    for (int sd = 0; sd < 2; ++sd) {
-                        const int sz = sd == 0 ? size0 : size1;
-                        if (sz == 0) continue;
-                        SubNode* ch = &nxt[slot++];
-                        for (int i = 0; i < D; ++i) {
-                            ch->c[i] = nd->c[i];
-                            ch->w[i] = nd->w[i];
-                            double lo = s_blo[i], hi = s_bhi[i];
-                            if (i == chosen) {
-                                ch->c[i] = s_hc[i][sd];
-                                ch->w[i] = s_hw[i];
-                                lo = s_hlo[i][sd];
-                                hi = s_hhi[i][sd];
-                            }
-                            ch->lo[i] = fmax(nd->lo[i], lo);
-                            ch->hi[i] = fmin(nd->hi[i], hi);
-                        }
-                        ch->start = sd == 0 ? off0 : off1;
-                        ch->count = sz;
-                    }
-                }
-                n_nxt += add;
-                dst_off = off1 + size1;
-            }
-            __syncthreads();
+            r[2 * KD + kFFlag] = ((double)wmax / 2.0 <= 2.0 && r[2 * KD + kFCount] <= 400) ? kNodeLeaf : kNodeSplit;
+            s_pos[node * 2] = 0;
+            s_pos[node * 2 + 1] = 0;
+            s_lsum[node * 3] = 0.0;
+            s_lsum[node * 3 + 1] = 0.0;
+            s_lsum[node * 3 + 2] = 0.0;
         }
-        // next level
-        SubNode* t = cur;
-        cur = nxt;
-        nxt = t;
-        n_cur = n_nxt;
+        __syncthreads();
+
+        // ---- A2, flat over the members of the level: per eligible dimension, how many members fall into each half
+        // (a member counts for dimension i when it is inside the node's box along every OTHER dimension).  A thread
+        // keeps kU members in flight: the voxel index and then its D offsets are dependent global loads (~1 us per
+        // member when taken one at a time, which is what bounded the kernel).
+        {
+            int node = 0;
+            for (int k0 = 0; k0 < total; k0 += kU * kSubThreads) {
+                int nodeu[kU], vox[kU];
+                bool valid[kU], work[kU];
+                unsigned in[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int k = k0 + u * kSubThreads + tid;
+                    valid[u] = k < total;
+                    if (valid[u])
+                        while (k >= start[node + 1]) ++node;
+                    nodeu[u] = node;
+                    vox[u] = valid[u] ? src[k] : 0;
+                    in[u] = 0;
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) work[u] = valid[u] && ni[(size_t)nodeu[u] * NI + 2 * KD + kFFlag] == kNodeSplit;
+                for (int i = 0; i < D; ++i) {
+                    double v[kU];
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) v[u] = p.off1[(size_t)vox[u] * D + i];       // independent loads
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const double* bd = nd + (size_t)nodeu[u] * ND + 2 * KD + 6 * i;
+                        if (work[u] && v[u] >= bd[0] && v[u] <= bd[1]) in[u] |= 1u << i;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int nu = nodeu[u];
+                    const int32_t* r = ni + (size_t)nu * NI;
+                    const double* o = p.off1 + (size_t)vox[u] * D;
+                    // whole warp inside one node (the common case: lists are contiguous): vote, one atomic per tally
+                    const int n0 = __shfl_sync(0xffffffffu, nu, 0);
+                    const bool uniform = __all_sync(0xffffffffu, !valid[u] || nu == n0);
+                    const unsigned missing = all & ~in[u];
+                    const bool maybe = work[u] && !(missing & (missing - 1));   // outside along two dimensions: nowhere
+                    if (uniform) {
+                        const int32_t* r0 = ni + (size_t)n0 * NI;
+                        if (r0[2 * KD + kFFlag] != kNodeSplit) continue;         // uniform
+                        const double* bd0 = nd + (size_t)n0 * ND + 2 * KD;
+                        for (int i = 0; i < D; ++i) {
+                            if (r0[KD + i] < 6) continue;                        // not eligible (w / 2 < 3), uniform
+                            bool h0 = false, h1 = false;
+                            if (maybe && ((in[u] | (1u << i)) == all)) {
+                                const double v = o[i];
+                                h0 = v >= bd0[6 * i + 2] && v <= bd0[6 * i + 3];
+                                h1 = v >= bd0[6 * i + 4] && v <= bd0[6 * i + 5];
+                            }
+                            const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+                            if (lane == 0) {
+                                if (m0) atomicAdd(&s_cnt[(n0 * KD + i) * 2], __popc(m0));
+                                if (m1) atomicAdd(&s_cnt[(n0 * KD + i) * 2 + 1], __popc(m1));
+                            }
+                        }
+                    } else if (maybe) {
+                        const double* bd = nd + (size_t)nu * ND + 2 * KD;
+                        for (int i = 0; i < D; ++i) {
+                            if (r[KD + i] < 6 || ((in[u] | (1u << i)) != all)) continue;
+                            const double v = o[i];
+                            if (v >= bd[6 * i + 2] && v <= bd[6 * i + 3]) atomicAdd(&s_cnt[(nu * KD + i) * 2], 1);
+                            if (v >= bd[6 * i + 4] && v <= bd[6 * i + 5]) atomicAdd(&s_cnt[(nu * KD + i) * 2 + 1], 1);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- B1, one thread per node: the reference's choice (:264-331): most balanced split, dimensions still wider
+        // than 2 first; (:333-335) "min_patch is None or len(two_patches) == 0" -- two_patches of the LAST dimension tried
+        for (int node = tid; node < n_cur; node += kSubThreads) {
+            int32_t* r = ni + (size_t)node * NI;
+            if (r[2 * KD + kFFlag] == kNodeLeaf) continue;
+            int best = -1, best_diff = 2500000, last = -1;
+            bool keep8 = false;
+            for (int i = 0; i < D; ++i) {
+                const DimBounds b = dim_bounds(r[i], r[KD + i]);
+                if (!b.elig) continue;
+                last = i;
+                const int diff = abs(s_cnt[(node * KD + i) * 2] - s_cnt[(node * KD + i) * 2 + 1]);
+                if (b.hw > 2) {
+                    if (!keep8) {
+                        best_diff = diff;
+                        best = i;
+                        keep8 = true;
+                    } else if (diff < best_diff) {
+                        best_diff = diff;
+                        best = i;
+                    }
+                } else if (!keep8 && diff < best_diff) {
+                    best_diff = diff;
+                    best = i;
+                }
+            }
+            if (best < 0 || last < 0 || (s_cnt[(node * KD + last) * 2] == 0 && s_cnt[(node * KD + last) * 2 + 1] == 0)) {
+                r[2 * KD + kFFlag] = kNodeLeaf;
+            } else {
+                r[2 * KD + kFChosen] = best;
+                r[2 * KD + kFSize0] = s_cnt[(node * KD + best) * 2];
+                r[2 * KD + kFSize1] = s_cnt[(node * KD + best) * 2 + 1];
+            }
+        }
+        __syncthreads();
+
+        // ---- B2, one thread: leaf numbers, child slots and list offsets in node order (the reference's order)
+        if (tid == 0) {
+            int n_leaf = s_state[0], status = s_state[1], n_nxt = 0, dst_off = 0;
+            for (int node = 0; node < n_cur; ++node) {
+                int32_t* r = ni + (size_t)node * NI;
+                if (r[2 * KD + kFFlag] == kNodeLeaf) {
+                    r[2 * KD + kFSlot] = n_leaf;
+                    if (n_leaf >= q.max_leaves) status = 3;
+                    ++n_leaf;
+                    continue;
+                }
+                const int size0 = r[2 * KD + kFSize0], size1 = r[2 * KD + kFSize1];
+                const int add = (size0 > 0 ? 1 : 0) + (size1 > 0 ? 1 : 0);
+                if (dst_off + size0 + size1 > kListCap) {
+                    status = 1;
+                    r[2 * KD + kFFlag] = kNodeDropped;
+                } else if (n_nxt + add > NN) {
+                    status = 2;
+                    r[2 * KD + kFFlag] = kNodeDropped;
+                } else {
+                    r[2 * KD + kFSlot] = n_nxt;
+                    r[2 * KD + kFOff0] = dst_off;
+                    if (size0 > 0) start_nxt[n_nxt++] = dst_off;
+                    if (size1 > 0) start_nxt[n_nxt++] = dst_off + size0;
+                    dst_off += size0 + size1;
+                }
+            }
+            start_nxt[n_nxt] = dst_off;
+            s_state[0] = n_leaf;
+            s_state[1] = status;
+            s_state[2] = n_nxt;
+        }
+        __syncthreads();
+
+        // ---- B3, one thread per node: leaf records / child node records
+        for (int node = tid; node < n_cur; node += kSubThreads) {
+            const int32_t* r = ni + (size_t)node * NI;
+            const double* rd = nd + (size_t)node * ND;
+            const int flag = r[2 * KD + kFFlag];
+            if (flag == kNodeLeaf) {
+                const int slot = r[2 * KD + kFSlot];
+                if (slot < q.max_leaves) {
+                    const size_t lb = (size_t)cand * q.max_leaves + slot;
+                    for (int i = 0; i < D; ++i) {
+                        q.leaf_off[lb * D + i] = r[i];
+                        q.leaf_w[lb * D + i] = r[KD + i];
+                        q.leaf_box[(lb * 2 + 0) * D + i] = rd[i];
+                        q.leaf_box[(lb * 2 + 1) * D + i] = rd[KD + i];
+                    }
+                    q.leaf_npts[lb] = r[2 * KD + kFCount];
+                }
+            } else if (flag == kNodeSplit) {
+                const int chosen = r[2 * KD + kFChosen];
+                int slot = r[2 * KD + kFSlot];
+                for (int sd = 0; sd < 2; ++sd) {
+                    const int sz = r[2 * KD + (sd == 0 ? kFSize0 : kFSize1)];
+                    if (sz == 0) continue;
+                    int32_t* ch = ni_nxt + (size_t)slot * NI;
+                    double* chd = nd_nxt + (size_t)slot * ND;
+                    for (int i = 0; i < D; ++i) {
+                        const DimBounds b = dim_bounds(r[i], r[KD + i]);
+                        int c = r[i], w = r[KD + i];
+                        double lo = b.blo, hi = b.bhi;
+                        if (i == chosen) {
+                            c = sd == 0 ? b.hc0 : b.hc1;
+                            w = b.hw;
+                            lo = sd == 0 ? b.hlo0 : b.hlo1;
+                            hi = sd == 0 ? b.hhi0 : b.hhi1;
+                        }
+                        ch[i] = c;
+                        ch[KD + i] = w;
+                        chd[i] = fmax(rd[i], lo);
+                        chd[KD + i] = fmin(rd[KD + i], hi);
+                    }
+                    ch[2 * KD + kFStart] = start_nxt[slot];
+                    ch[2 * KD + kFCount] = sz;
+                    ++slot;
+                }
+            }
+        }
+        // ---- C, flat over the members: children's member lists (a member within 1e-3 of the split plane goes to both
+        // halves); position sums of the leaves' members for Patch.center_pos().  kU members in flight as above.
+        {
+            int node = 0;
+            for (int k0 = 0; k0 < total; k0 += kU * kSubThreads) {
+                int nodeu[kU], vox[kU], flag[kU], chosen[kU];
+                bool valid[kU], others[kU];
+                double vi[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int k = k0 + u * kSubThreads + tid;
+                    valid[u] = k < total;
+                    if (valid[u])
+                        while (k >= start[node + 1]) ++node;
+                    nodeu[u] = node;
+                    vox[u] = valid[u] ? src[k] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int32_t* r = ni + (size_t)nodeu[u] * NI;
+                    flag[u] = valid[u] ? r[2 * KD + kFFlag] : kNodeDropped;
+                    chosen[u] = flag[u] == kNodeSplit ? r[2 * KD + kFChosen] : -1;
+                    others[u] = flag[u] == kNodeSplit;
+                    vi[u] = 0.0;
+                }
+                bool any_split = false;
+#pragma unroll
+                for (int u = 0; u < kU; ++u) any_split = any_split || flag[u] == kNodeSplit;
+                if (any_split)
+                    for (int i = 0; i < D; ++i) {
+                        double v[kU];
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) v[u] = p.off1[(size_t)vox[u] * D + i];   // independent loads
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) {
+                            if (i == chosen[u]) {
+                                vi[u] = v[u];
+                            } else {
+                                const double* bd = nd + (size_t)nodeu[u] * ND + 2 * KD + 6 * i;
+                                others[u] = others[u] && (v[u] >= bd[0]) && (v[u] <= bd[1]);
+                            }
+                        }
+                    }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int nu = nodeu[u];
+                    const int32_t* r = ni + (size_t)nu * NI;
+                    bool in0 = false, in1 = false;
+                    if (flag[u] == kNodeSplit) {
+                        const double* bc = nd + (size_t)nu * ND + 2 * KD + 6 * chosen[u];
+                        in0 = others[u] && vi[u] >= bc[2] && vi[u] <= bc[3];
+                        in1 = others[u] && vi[u] >= bc[4] && vi[u] <= bc[5];
+                    }
+                    double sx = 0.0, sy = 0.0, sz = 0.0;
+                    const bool centre = flag[u] == kNodeLeaf && q.leaf_centre != nullptr;
+                    if (centre) {
+                        const int iz = vox[u] % p.Nz, r2 = vox[u] / p.Nz;
+                        const int ix = r2 % p.Nx1, iy = r2 / p.Nx1;
+                        sx = q.grid1[ix];
+                        sy = q.grid1[p.Nx1 + iy];
+                        sz = q.grid1[p.Nx1 + p.Ny1 + iz];
+                    }
+                    const int n0 = __shfl_sync(0xffffffffu, nu, 0);
+                    const bool uniform = __all_sync(0xffffffffu, !valid[u] || nu == n0);
+                    if (uniform) {
+                        const int32_t* r0 = ni + (size_t)n0 * NI;
+                        const int f0 = r0[2 * KD + kFFlag];
+                        if (f0 == kNodeSplit) {                                  // warp-aggregated append
+                            const unsigned m0 = __ballot_sync(0xffffffffu, in0), m1 = __ballot_sync(0xffffffffu, in1);
+                            int b0 = 0, b1 = 0;
+                            if (lane == 0) {
+                                if (m0) b0 = atomicAdd(&s_pos[n0 * 2], __popc(m0));
+                                if (m1) b1 = atomicAdd(&s_pos[n0 * 2 + 1], __popc(m1));
+                            }
+                            b0 = __shfl_sync(0xffffffffu, b0, 0);
+                            b1 = __shfl_sync(0xffffffffu, b1, 0);
+                            const unsigned below = (1u << lane) - 1;
+                            const int off0 = r0[2 * KD + kFOff0], off1 = off0 + r0[2 * KD + kFSize0];
+                            if (in0) dst[off0 + b0 + __popc(m0 & below)] = vox[u];
+                            if (in1) dst[off1 + b1 + __popc(m1 & below)] = vox[u];
+                        } else if (f0 == kNodeLeaf && q.leaf_centre != nullptr) {
+#pragma unroll
+                            for (int d = 16; d > 0; d >>= 1) {
+                                sx += __shfl_xor_sync(0xffffffffu, sx, d);
+                                sy += __shfl_xor_sync(0xffffffffu, sy, d);
+                                sz += __shfl_xor_sync(0xffffffffu, sz, d);
+                            }
+                            if (lane == 0) {
+                                atomicAdd(&s_lsum[n0 * 3], sx);
+                                atomicAdd(&s_lsum[n0 * 3 + 1], sy);
+                                atomicAdd(&s_lsum[n0 * 3 + 2], sz);
+                            }
+                        }
+                    } else {
+                        if (flag[u] == kNodeSplit) {
+                            const int off0 = r[2 * KD + kFOff0], off1 = off0 + r[2 * KD + kFSize0];
+                            if (in0) dst[off0 + atomicAdd(&s_pos[nu * 2], 1)] = vox[u];
+                            if (in1) dst[off1 + atomicAdd(&s_pos[nu * 2 + 1], 1)] = vox[u];
+                        } else if (centre) {
+                            atomicAdd(&s_lsum[nu * 3], sx);
+                            atomicAdd(&s_lsum[nu * 3 + 1], sy);
+                            atomicAdd(&s_lsum[nu * 3 + 2], sz);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- D, one thread per node: Patch.center_pos() of the leaves (np.mean of area_points; the sums above are
+        // accumulated in double in arbitrary order: differences of a few ulp between runs)
+        if (q.leaf_centre)
+            for (int node = tid; node < n_cur; node += kSubThreads) {
+                const int32_t* r = ni + (size_t)node * NI;
+                const int slot = r[2 * KD + kFSlot], cnt = r[2 * KD + kFCount];
+                if (r[2 * KD + kFFlag] != kNodeLeaf || slot >= q.max_leaves) continue;
+                for (int a = 0; a < 3; ++a)
+                    q.leaf_centre[((size_t)cand * q.max_leaves + slot) * 3 + a] =
+                        cnt > 0 ? s_lsum[node * 3 + a] / (double)cnt : nan("");
+            }
+        n_cur = s_state[2];
         src = dst;
         ++level;
         __syncthreads();
     }
     if (tid == 0) {
-        q.leaf_count[cand] = n_leaf;
-        q.status[cand] = status;
+        q.leaf_count[cand] = s_state[0];
+        q.status[cand] = s_state[1];
     }
 }
 
@@ -781,6 +1054,43 @@ __global__ void build_shift_table_kernel(const int32_t* __restrict__ cnt, const 
             if (ch == 0) mix_index[n] = b;
         }
     }
+}
+
+template <typename T>
+int grow_scratch(T** ptr, size_t* cap, size_t need, const char* what) {
+    if (need <= *cap) return ASW_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc(ptr, need * sizeof(T));
+    if (e != cudaSuccess) {
+        set_error("asw_subdivide: %s of %zu bytes: %s", what, need * sizeof(T), cudaGetErrorString(e));
+        return ASW_ERR_ALLOC;
+    }
+    *cap = need;
+    return ASW_OK;
+}
+
+template <int KD>
+int launch_subdivide(asw_select* h, SubParams& q, int n, cudaStream_t stream) {
+    using C = SubCfg<KD>;
+    int rc;
+    if ((rc = grow_scratch(&h->d_nodes_i, &h->nodes_i_cap, (size_t)n * 2 * C::kNodes * C::kNI, "node scratch")) != ASW_OK) return rc;
+    if ((rc = grow_scratch(&h->d_nodes_d, &h->nodes_d_cap, (size_t)n * 2 * C::kNodes * C::kND, "node scratch")) != ASW_OK) return rc;
+    q.nodes_i = h->d_nodes_i;
+    q.nodes_d = h->d_nodes_d;
+    const size_t smem = C::smem_bytes();
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(subdivide_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // enough carve-out for the resident CTAs the register budget allows (the default fits fewer)
+        int pct = (int)((C::kCtasPerSm * (smem + 4096) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
+        if (pct > 100) pct = 100;
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(subdivide_kernel<KD>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
+    subdivide_kernel<KD><<<n, C::kThreads, smem, stream>>>(q);
+    ASW_LAUNCH_CHECK("subdivide_kernel");
+    return ASW_OK;
 }
 
 // Fine-stage shift table (the patch-list assembly of Spotform_Small_Patch_Parallel, sep/Mic_Array.py:244-262): every
@@ -889,6 +1199,9 @@ static void fill_geometry(const asw_select* h, SelectParams& p) {
     p.Nx1 = h->Nx1;
     p.Nz = h->Nz;
     p.box_table = h->d_box;
+    p.cell = h->d_cell;
+    p.ncx = h->ncx;
+    p.ncy = h->ncy;
 }
 
 extern "C" {
@@ -904,6 +1217,10 @@ int asw_select_create(asw_select_t** out, int device, int G, int D, int W, const
         return ASW_ERR_ARG;
     }
     *out = nullptr;
+    if (Nx1 > 4095 || Ny1 > 4095 || Nz > 255) {
+        set_error("asw_select_create: 1 cm volume %d x %d x %d exceeds the packed index range (4095 x 4095 x 255)", Nx1, Ny1, Nz);
+        return ASW_ERR_RANGE;
+    }
     ASW_CUDA_CHECK(cudaSetDevice(device));
     asw_select* h = new asw_select();
     h->device = device;
@@ -961,6 +1278,23 @@ int asw_select_create(asw_select_t** out, int device, int G, int D, int W, const
         }
         h->d_box = box;
     }
+    {
+        h->ncx = (Nx1 + kCell - 1) / kCell;
+        h->ncy = (Ny1 + kCell - 1) / kCell;
+        const long long cells = (long long)h->ncx * h->ncy * Nz;
+        e = cudaMalloc(&h->d_cell, sizeof(float) * 2 * (size_t)cells * D);
+        if (e == cudaSuccess) {
+            cell_bounds_kernel<<<(unsigned)((cells + 127) / 128), 128>>>(h->d_off1, Ny1, Nx1, Nz, D, h->ncy, h->ncx, h->d_cell);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            count_launch();
+        }
+        if (e != cudaSuccess) {
+            set_error("asw_select_create: cell bounds: %s", cudaGetErrorString(e));
+            asw_select_destroy(h);
+            return ASW_ERR_CUDA;
+        }
+    }
     *out = h;
     return ASW_OK;
 }
@@ -978,7 +1312,10 @@ int asw_select_destroy(asw_select_t* h) {
     cudaFree(h->d_yy5);
     cudaFree(h->d_off1);
     cudaFree(h->d_box);
+    cudaFree(h->d_cell);
     cudaFree(h->d_lists);
+    cudaFree(h->d_nodes_i);
+    cudaFree(h->d_nodes_d);
     delete h;
     return ASW_OK;
 }
@@ -1053,9 +1390,9 @@ int asw_subdivide(asw_select_t* h, const int32_t* centres_dev, const int32_t* wi
         set_error("asw_subdivide: null argument or bad shape");
         return ASW_ERR_ARG;
     }
-    if (h->D > kSubD) {
+    if (h->D > kMaxD) {
         set_error("asw_subdivide: %d TDoA dimensions exceed the device path's limit of %d (use the host path)", h->D,
-                  kSubD);
+                  kMaxD);
         return ASW_ERR_RANGE;
     }
     if (n == 0) return ASW_OK;
@@ -1091,14 +1428,9 @@ int asw_subdivide(asw_select_t* h, const int32_t* centres_dev, const int32_t* wi
     q.grid1 = h->d_grid1;
     q.root_after = root_after_dev;
     q.status = status_dev;
-    const size_t smem = 2 * (size_t)kMaxNodes * sizeof(SubNode);
-    static PerDeviceOnce attr_once;
-    if (attr_once.need()) {
-        ASW_CUDA_CHECK(cudaFuncSetAttribute(subdivide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    subdivide_kernel<<<n, kSubThreads, smem, (cudaStream_t)stream>>>(q);
-    ASW_LAUNCH_CHECK("subdivide_kernel");
-    return ASW_OK;
+    if (h->D <= 8) return launch_subdivide<8>(h, q, n, (cudaStream_t)stream);
+    if (h->D <= 16) return launch_subdivide<16>(h, q, n, (cudaStream_t)stream);
+    return launch_subdivide<32>(h, q, n, (cudaStream_t)stream);
 }
 
 int asw_build_fine_table(const int32_t* leaf_count_dev, const int32_t* leaf_off_dev, const int32_t* root_after_dev,

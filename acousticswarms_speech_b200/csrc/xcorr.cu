@@ -17,7 +17,7 @@
 //   sum_k a_s[k] b_s[k + j] for j in [0, 2L] never wraps inside the 2048-point circular correlation, so
 //   R_cc'(j - L) = IFFT_2048( sum_s conj(A_s) B_s )[j].
 //   K1 xcorr_fft_kernel    one warp per (mixture, block, role/channel): quantise, FFT-2048 (packed 1024-point complex),
-//                          real-input split for ALL bins -> spectra in global memory (L2 resident: the launch is chunked)
+//                          real-input split for ALL bins -> spectra in global memory
 //   K2 xcorr_pair_kernel   thread = bin, 4 x 8 pair tiles in registers, blocks summed in groups -> partial cross-spectra
 //   K3 xcorr_inverse_kernel one warp per (mixture, pair): sum the groups, inverse real FFT, lags -L..L as float64
 //   S_c and E_c (float64, exact: 16-bit values, 30-bit products) ride along: every sample belongs to exactly one
@@ -52,7 +52,7 @@ constexpr int kTile = 2 * 32 * 33;             // floats of one warp's transpose
 constexpr int kBlocksPerGroup = 8;             // blocks summed by one pair CTA
 constexpr int kPairThreads = 256;
 constexpr int kTI = 4, kTJ = 8, kMaxTiles = 24;
-constexpr size_t kSpecBudget = 48u << 20;      // spectra of one chunk stay inside the 126 MB L2
+constexpr size_t kSpecBudget = 512u << 20;     // spectra workspace per chunk of mixtures (see asw_corr_tables)
 
 __device__ __forceinline__ float quant16(float x) { return rintf(x * 32768.f) * (1.f / 32768.f); }
 
@@ -426,6 +426,9 @@ int asw_corr_tables(asw_corr_t* h, const float* mix_dev, int B, int T, double* t
     p.P = h->P;
     p.stride = asw_corr_table_len(h);
     p.vec = (T % 2 == 0) && ((reinterpret_cast<uintptr_t>(mix_dev) & 7) == 0);
+    // Chunking: the spectra (14 MB per mixture at 7 mics / 3 s) are written by K1 and read once by K2.  Chunks small
+    // enough to stay in L2 (3 mixtures) were measured slower than one large launch per 36 mixtures: 11 x 3 small
+    // launches with tails against 3, while the extra HBM traffic is ~5 us per mixture.
     const size_t spec_per = (size_t)p.nblk * p.U2 * kNc;          // float2 per mixture
     int chunk = (int)(kSpecBudget / (spec_per * sizeof(float2)));
     if (chunk < 1) chunk = 1;

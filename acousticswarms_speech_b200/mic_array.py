@@ -111,9 +111,15 @@ class Mic_Array(object):
         for c in candidates:
             if not np.all(np.asarray(c.width_list) == c.width_list[0]):
                 raise native._lib.AswError("coarse patches must have one width in every dimension")
-        cn, off, wid, npts, box, root, centre, members = native.subdivide(
-            node.native_select, torch.from_numpy(centres).to(dev), torch.from_numpy(widths).to(dev),
-            self.upper_bound_pairwise, member_cap=1 << 17)
+        for max_leaves in (128, 1024, 8192):     # many-mic arrays split along more dimensions: retry with longer lists
+            try:
+                cn, off, wid, npts, box, root, centre, members = native.subdivide(
+                    node.native_select, torch.from_numpy(centres).to(dev), torch.from_numpy(widths).to(dev),
+                    self.upper_bound_pairwise, max_leaves=max_leaves, member_cap=1 << 17)
+                break
+            except native._lib.AswCapacityError:
+                if max_leaves == 8192:
+                    raise
         pos1 = node.Pos_1.reshape(-1, 3)
         out = []
         for i, cand in enumerate(candidates):
@@ -154,7 +160,7 @@ class Mic_Array(object):
         width_list0 = [2 for _ in range(self.num_mic - 1)]
         total_patch, patches_indexes, init_area_total, centre_total = [], [0], [], []
         self.spotforming_times = 0
-        on_device = (self.SRP_node.native is not None and self.num_mic - 1 <= 8 and len(candidate_finished) > 0)
+        on_device = (self.SRP_node.native is not None and self.num_mic - 1 <= 31 and len(candidate_finished) > 0)
         fine_lists = self._search_area_device(candidate_finished) if on_device else None
         for ci, cand in enumerate(candidate_finished):
             if on_device:

@@ -241,13 +241,15 @@ class C2Pipeline:
         self.mode = "plain"          # "plain" | "norm" (fused normalize_input from correlation tables) | "norm_exact"
         self.corr = None
         self.corr_tabs = None
+        self.max_lag = MAX_LAG
         self.stage_events = []
         self.launched_patches = []   # patches covered by every timed shift-stack launch (count-sync mode)
 
     def enable_norm(self):
         from acousticswarms_speech_b200 import native
         if self.corr is None:
-            self.corr = native.CorrTables(self.M, self.dev, max_lag=MAX_LAG)
+            self.max_lag = native.CorrTables.lag_for_geometry(self.node.mic_pos, self.node.FS)
+            self.corr = native.CorrTables(self.M, self.dev, max_lag=self.max_lag)
             self.corr_tabs = [self.torch.empty((self.B, self.corr.table_len), device=self.dev, dtype=self.torch.float64)
                               for _ in range(2)]
 
@@ -340,8 +342,8 @@ class C2Pipeline:
                 fe.stack_counted(src, shifts_dev, mi_dev, ntot_dev, n_rows, events=events)
             else:
                 fe.stack_norm_counted(src, shifts_dev, mi_dev, ntot_dev, n_rows,
-                                      tables=self.corr_tabs[slot] if self.mode == "norm" else None, max_lag=MAX_LAG,
-                                      events=events)
+                                      tables=self.corr_tabs[slot] if self.mode == "norm" else None,
+                                      max_lag=self.max_lag, events=events)
             self.table_free[slot] = torch.cuda.Event()
             self.table_free[slot].record(sstream)
             if timing_stages:
@@ -538,7 +540,11 @@ def run_b200(args, rank, world):
         torch.cuda.synchronize()
         pipe.serial = saved[0]
         k = [(a.elapsed_time(b), n) for a, b, n in events]
-        full = [t for t, n in k if n == fe.net_batch]
+        if pipe.count_sync:
+            full = [t for t, n in k if n == fe.net_batch]
+        else:       # capacity-sized launches: only those whose 128 rows all lie below the sub-batch's patch count
+            per = (cap + fe.net_batch - 1) // fe.net_batch
+            full = [t for i, (t, n) in enumerate(k) if ((i % per) + 1) * fe.net_batch <= n_per[((i // per) % NSUB) % NU]]
         st = pipe.stage_events[1:] or pipe.stage_events
         out = {"avg_launch_ms": sum(full) / max(1, len(full)), "full_launches_timed": len(full),
                "score_ms": sum(e[0].elapsed_time(e[1]) for e in st) / len(st),
@@ -751,7 +757,8 @@ def bench_c3(args, fe, node, mix_devs, dev, pk, reduce_max, barrier, world):
     groups = groups[:NMIX // GB]
     P = node.native_select.max_patches
     cap = GB * 1280
-    corr = native.CorrTables(M, dev, max_lag=MAX_LAG)
+    max_lag = native.CorrTables.lag_for_geometry(node.mic_pos, node.FS)
+    corr = native.CorrTables(M, dev, max_lag=max_lag)
     front_stream, stack_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     fe_fine = type(fe)(node, dev, net_batch=fe.net_batch, ring=2)      # its own ring and map buffers
 
@@ -789,7 +796,7 @@ def bench_c3(args, fe, node, mix_devs, dev, pk, reduce_max, barrier, world):
             stack_stream.wait_event(cur["ev"])
             with torch.cuda.stream(stack_stream):
                 fe_fine.stack_norm_counted(cur["x"], cur["shifts"], cur["mi"], cur["ntot"], n, tables=cur["tabs"],
-                                           max_lag=MAX_LAG, events=events)
+                                           max_lag=max_lag, events=events)
                 done = torch.cuda.Event()
                 done.record(stack_stream)
             if serial:
@@ -835,7 +842,7 @@ def bench_c3(args, fe, node, mix_devs, dev, pk, reduce_max, barrier, world):
     assert (sh0[:, 0] == 0).all() and mi0.min() >= 0 and mi0.max() < GB and (np.diff(mi0) >= 0).all()
     return {"workload": "C3: fine width-2 Spotform_Small_Patch_Parallel refinement over surviving hypercubes, 64 mixtures per GPU, "
                         "7 mics, 3 s @ 48 kHz", "mixtures_per_gpu": NMIX, "fine_patches_per_gpu": total,
-            "fine_patches_per_mixture": total / NMIX, "ms_per_pass": ms, "patches_per_s": world * total / (ms / 1e3),
+            "fine_patches_per_mixture": total / NMIX, "ms_per_pass": ms, "corr_table_max_lag": max_lag, "patches_per_s": world * total / (ms / 1e3),
             "hbm": {"algorithmic_bytes": byts, "achieved_gbs": byts / (ms / 1e3) / 1e9,
                     "frac": byts / (ms / 1e3) / 1e9 / pk["hbm_gbs"],
                     "kernel_avg_launch_ms": k_ms, "kernel_achieved_gbs": 4.0 * fe.net_batch * M * T / (k_ms / 1e3) / 1e9,

@@ -194,8 +194,8 @@ int asw_shift_stack_norm(const float* mix_dev, const int32_t* shifts_dev, const 
  * pass to ~1e-6 relative (bar: 1e-4); results are reproducible bit for bit.
  *   asw_corr_create: max_lag in 1..512 samples (48 kHz: 3.6 m of aperture); M in 2..32
  *   asw_corr_tables: mix_dev [B][M][T] float32, T >= 4096; tables_dev [B][asw_corr_table_len] float64 out.
- * The handle owns the spectrum workspace (<= 48 MB: the batch is processed in L2-sized chunks); it is
- * single-stream and not re-entrant. */
+ * The handle owns the spectrum workspace (14 MB per mixture at 7 mics / 3 s, at most 512 MB: larger batches are
+ * processed in chunks); it is single-stream and not re-entrant. */
 typedef struct asw_corr asw_corr_t;
 int asw_corr_create(asw_corr_t** out, int device, int M, int max_lag);
 int asw_corr_destroy(asw_corr_t* h);

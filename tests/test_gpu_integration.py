@@ -563,6 +563,46 @@ def test_device_subdivision_equals_oracle_at_c2_size(cuda_device, desk):
     assert n_leaves > 1000
 
 
+@pytest.mark.parametrize("n_mics,seed", [(10, 3), (16, 4), (18, 5)])
+def test_device_subdivision_beyond_nine_mics_equals_oracle(cuda_device, n_mics, seed):
+    """asw_subdivide's 16- and 32-dimension instantiations (10 .. 32 mics: BASELINE config C5's 16-mic array) against
+    oracle/subdivide_oracle.py on a small room: device pruning, then every coarse patch subdivided on the device vs
+    the oracle's search_area on its own patches -- leaves, order, index and the check_out mutation identical."""
+    import copy
+    from oracle import subdivide_oracle
+    from acousticswarms_speech_b200.mic_array import Mic_Array
+    from acousticswarms_speech_b200.pipeline import FrontEnd
+    scene = synth.small_scene(n_mics=n_mics, seed=seed)
+    scene.roi = [0.6, 1.5, -0.45, 0.45, 0.0, 0.5]
+    ma = Mic_Array(scene.mic_positions, Spk_Range=scene.roi)
+    fe = FrontEnd(ma.SRP_node)
+    geo = oracle_geometry(scene)
+    assert np.array_equal(geo.grids, ma.SRP_node.grids)
+    mixes = synth.mixtures(scene, 2, 72000, seeds=[seed, seed + 10])
+    smap = fe.score(torch.from_numpy(mixes).cuda())[0]
+    dev_lists = fe.prune(smap)
+    maps = smap.cpu().numpy()
+    n_leaves = 0
+    for b in range(mixes.shape[0]):
+        opatches = opatches_of(geo, maps[b], scene)
+        assert [list(p.sample_offset) for p in dev_lists[b]] == [list(p.sample_offset) for p in opatches]
+        assert [list(p.width_list) for p in dev_lists[b]] == [list(p.width_list) for p in opatches]
+        cands, ocands = copy.deepcopy(dev_lists[b][:10]), copy.deepcopy(opatches[:10])
+        total, index, _, _ = ma.small_patch_list(cands)
+        ototal, oindex = subdivide_oracle.small_patch_list(ocands, scene.mic_positions)
+        assert index == oindex
+        assert [list(p.sample_offset) for p in total] == [list(p.sample_offset) for p in ototal]
+        assert [list(p.width_list) for p in total] == [list(p.width_list) for p in ototal]
+        assert [list(c.sample_offset) for c in cands] == [list(c.sample_offset) for c in ocands]
+        assert [list(c.width_list) for c in cands] == [list(c.width_list) for c in ocands]
+        for a, o in list(zip(total, ototal))[::5]:
+            ca, co = a.center_pos(), o.center_pos()
+            assert (ca is None) == (co is None) and (co is None or np.abs(ca - co).max() <= 1e-12)
+            assert a.area_size() == o.area_size()
+        n_leaves += len(total)
+    assert n_leaves > 20
+
+
 class HalfMeanNet(torch.nn.Module):
     """The network whose DataParallelSpotModel reproduces oracle/make_golden.py's DelayAndSumSpot on 16-bit PCM content:
     (normalised mean over mics) x {1 coarse, 0.5 fine}; unnormalize restores the scale, the callers remove the mean."""
@@ -653,8 +693,13 @@ def test_capacity_guards(cuda_device, desk):
     n, off, wid, pk = fe.select(smap)
     shifts, mi, ntot = fe.shift_table(n, off, 5)
     assert int(ntot[0]) == 5 and shifts.shape == (5, 7)
-    # counted shift-stack honours n_base: rows [3, 5) are written, slot 2 of the output (row 5 >= n_total) is not
+    # counted shift-stack honours n_base: rows [3, 5) are written, slot 2 of the output (row 5 >= n_total) is not;
+    # rows beyond the table's capacity are refused on the host before anything is launched
     out = torch.full((3, 7, mix.shape[1]), -7.0, device="cuda")
+    with pytest.raises(_lib.AswError):
+        native.shift_stack_counted(torch.from_numpy(mix[None]).cuda(), shifts, mi, ntot, 3, 3, out)
+    shifts, mi, ntot = fe.shift_table(n, off, 6)
+    ntot.fill_(5)
     native.shift_stack_counted(torch.from_numpy(mix[None]).cuda(), shifts, mi, ntot, 3, 3, out)
     o = out.cpu().numpy()
     sh = shifts.cpu().numpy()
