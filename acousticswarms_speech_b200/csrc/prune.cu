@@ -33,11 +33,18 @@ namespace {
 
 constexpr int kMaxPeaksSort = 2048;
 
-__global__ void __launch_bounds__(1024) map_max_kernel(const float* __restrict__ map, int G, float* __restrict__ mx) {
+// MAX_POWER of every mixture; the same sweep resets the per-cluster "first peak rank" scratch of peak_flag_kernel, so a
+// call never depends on how the previous call on this handle ended.
+__global__ void __launch_bounds__(1024) map_max_kernel(const float* __restrict__ map, int G, float* __restrict__ mx,
+                                                        int* __restrict__ first) {
     __shared__ float s[32];
     const float* m = map + (size_t)blockIdx.x * G;
+    int* f = first + (size_t)blockIdx.x * G;
     float v = 0.f;   // the map is >= 0 by construction (:253)
-    for (int g = threadIdx.x; g < G; g += blockDim.x) v = fmaxf(v, m[g]);
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        v = fmaxf(v, m[g]);
+        f[g] = INT_MAX;
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
@@ -141,9 +148,6 @@ __global__ void __launch_bounds__(1024) peak_collect_kernel(int* __restrict__ fi
     if (threadIdx.x == 0) count[b] = total;
 }
 
-__global__ void fill_int_kernel(int* p, size_t n, int v) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
-}
 
 }  // namespace
 }  // namespace asw
@@ -222,10 +226,8 @@ int asw_peaks_find(asw_peaks_t* h, const float* map_dev, int B, int32_t* peaks_d
         h->Bcap = 0;
         ASW_CUDA_CHECK(cudaMalloc(&h->d_first, (size_t)B * h->G * sizeof(int)));
         h->Bcap = B;
-        fill_int_kernel<<<256, 256, 0, s>>>(h->d_first, (size_t)B * h->G, INT_MAX);
-        ASW_LAUNCH_CHECK("fill_int_kernel");
     }
-    map_max_kernel<<<B, 1024, 0, s>>>(map_dev, h->G, max_power_dev);
+    map_max_kernel<<<B, 1024, 0, s>>>(map_dev, h->G, max_power_dev, h->d_first);
     ASW_LAUNCH_CHECK("map_max_kernel");
     PeakParams p{};
     p.map = map_dev;

@@ -66,59 +66,107 @@ def si_sdr_from_gram(ee, rr, er):
 
 
 class DataParallelSpotModel(nn.Module):
+    """Drop-in for the reference's class (sep/training/JointModel/network.py:27-104).
+
+    Multi-GPU: the reference wraps the network in ``nn.DataParallel`` (:30), i.e. it stacks every 128-patch batch
+    (516 MB) on ONE device and scatters it over PCIe/NVLink each forward.  Here the PATCH LIST is sharded instead: every
+    visible device receives the 4 MB mixture once, stacks (and normalises) its own contiguous slice of the patches
+    right next to its replica of the network, and only the (n, T) outputs travel back.  Replicas are refreshed from the
+    primary module on every call (``torch.nn.parallel.replicate``, what ``nn.DataParallel`` does per forward)."""
+
     TABLE_MIN_PATCHES = 48      # below this the exact per-patch statistics pass is cheaper than building the tables
     TABLE_MAX_LAG = 512         # samples; patches with a larger pair lag take the exact pass on the device
+    SHARD_MIN_PATCHES = 2       # patches per device below which sharding is not worth a replica refresh
 
-    def __init__(self, model, use_fp16=False, batch_size=SPOT_BATCH_SIZE, device=None, data_parallel=True):
+    def __init__(self, model, use_fp16=False, batch_size=SPOT_BATCH_SIZE, device=None, data_parallel=True,
+                 device_ids=None):
         super().__init__()
-        multi = data_parallel and torch.cuda.device_count() > 1
-        self.model = nn.DataParallel(model) if multi else model
+        self.model = model
         self.batch_size = batch_size
         self.dtype = torch.bfloat16 if use_fp16 else torch.float32
         if use_fp16:
             self.model.to(torch.bfloat16)
         self._device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.to(self._device)
-        self._buf = None
-        self._corr = None
+        if device_ids is None:
+            device_ids = list(range(torch.cuda.device_count())) if data_parallel else [self._device.index]
+        primary = self._device.index if self._device.index is not None else torch.cuda.current_device()
+        self.device_ids = [primary] + [d for d in device_ids if d != primary]
+        self._bufs = {}
+        self._corr = {}
 
     @property
     def device(self):
         return self._device
 
-    def _shift_and_sep_device(self, input_channels, patch_list, Strict, save_input):
-        """network.py:37-101 up to (not including) the copy back: (N, T) results on the device."""
+    def _stack_and_separate(self, model, mix, shifts, Strict, save_input, results, saved):
+        """network.py:58-101 for the patches of ``shifts`` on the device ``mix`` lives on; fills ``results`` (n, T)."""
         B = self.batch_size
+        dev = mix.device
+        N = shifts.shape[0]
+        M, T = mix.shape
+        key = dev.index
+        if key not in self._bufs or self._bufs[key].shape != (B, M, T):
+            self._bufs[key] = torch.empty((B, M, T), device=dev, dtype=torch.float32)   # reused like `data` (:58)
+        buf = self._bufs[key]
+        cond = torch.zeros((B, 2), device=dev, dtype=self.dtype)
+        cond[:, 0 if Strict == 1 else 1] = 1                                  # :62-73
+        # per-mixture correlation tables: every patch's mean / std from a few look-ups instead of a pass over its
+        # samples (pays off from a few dozen patches on; fewer take the exact statistics pass)
+        tables = None
+        if N >= self.TABLE_MIN_PATCHES and T >= native.CorrTables.MIN_T and M >= 2:
+            if key not in self._corr or self._corr[key].M != M:
+                self._corr[key] = native.CorrTables(M, dev, max_lag=self.TABLE_MAX_LAG)
+            tables = self._corr[key].compute(mix)
+        for i in range(0, N, B):
+            n = min(B, N - i)
+            data_norm, means, stds = native.shift_stack_norm(mix, shifts[i:i + n], out=buf, tables=tables,
+                                                             max_lag=self.TABLE_MAX_LAG)
+            data_norm = data_norm[:n]
+            if save_input:
+                saved.append(unnormalize_input(data_norm, means, stds).cpu())
+            result = model(data_norm.to(self.dtype), cond[:n])
+            results[i:i + n] = unnormalize_input(result, means.to(self.dtype), stds.to(self.dtype))[:, 0]
+
+    def _shift_and_sep_device(self, input_channels, patch_list, Strict, save_input):
+        """network.py:37-101 up to (not including) the copy back: (N, T) results on the primary device."""
         N = len(patch_list)
         dev = self.device
         self.model.eval()
         with torch.no_grad():
             mix = input_channels.to(dev, dtype=torch.float32).contiguous()       # copy once (:55)
             M, T = mix.shape
-            if self._buf is None or self._buf.shape != (B, M, T):
-                self._buf = torch.empty((B, M, T), device=dev, dtype=torch.float32)   # reused like `data` (:58)
             results = torch.zeros((N, T), device=dev, dtype=self.dtype)
-            cond = torch.zeros((B, 2), device=dev, dtype=self.dtype)
-            cond[:, 0 if Strict == 1 else 1] = 1                                  # :62-73
-            shifts = torch.from_numpy(native.offsets_to_shifts(
-                np.stack([p.sample_offset for p in patch_list]) if N else np.zeros((0, M - 1)))).to(dev)
-            # per-mixture correlation tables: every patch's mean / std from a few look-ups instead of a pass over its
-            # samples (pays off from a few dozen patches on; fewer take the exact statistics pass)
-            tables = None
-            if N >= self.TABLE_MIN_PATCHES and T >= native.CorrTables.MIN_T and M >= 2:
-                if self._corr is None or self._corr.M != M:
-                    self._corr = native.CorrTables(M, dev, max_lag=self.TABLE_MAX_LAG)
-                tables = self._corr.compute(mix)
+            shifts_host = torch.from_numpy(native.offsets_to_shifts(
+                np.stack([p.sample_offset for p in patch_list]) if N else np.zeros((0, M - 1))))
             saved = []
-            for i in range(0, N, B):
-                n = min(B, N - i)
-                data_norm, means, stds = native.shift_stack_norm(mix, shifts[i:i + n], out=self._buf, tables=tables,
-                                                                 max_lag=self.TABLE_MAX_LAG)
-                data_norm = data_norm[:n]
-                if save_input:
-                    saved.append(unnormalize_input(data_norm, means, stds).cpu())
-                result = self.model(data_norm.to(self.dtype), cond[:n])
-                results[i:i + n] = unnormalize_input(result, means.to(self.dtype), stds.to(self.dtype))[:, 0]
+            ids = self.device_ids if N >= self.SHARD_MIN_PATCHES * len(self.device_ids) else self.device_ids[:1]
+            if len(ids) == 1:
+                self._stack_and_separate(self.model, mix, shifts_host.to(dev), Strict, save_input, results, saved)
+            else:
+                # contiguous slices of the patch list, one per device; everything below is asynchronous per device, the
+                # host only issues work, so the devices run concurrently
+                replicas = torch.nn.parallel.replicate(self.model, ids, detach=True)
+                bounds = [(N * k) // len(ids) for k in range(len(ids) + 1)]
+                parts = []
+                ready = torch.cuda.Event()
+                ready.record(torch.cuda.current_stream(dev))
+                for k, d in enumerate(ids):
+                    lo, hi = bounds[k], bounds[k + 1]
+                    ddev = torch.device("cuda", d)
+                    with torch.cuda.device(ddev):
+                        torch.cuda.current_stream(ddev).wait_event(ready)
+                        mix_d = mix if d == dev.index else mix.to(ddev, non_blocking=True)
+                        part = results[lo:hi] if d == dev.index else torch.zeros((hi - lo, T), device=ddev, dtype=self.dtype)
+                        self._stack_and_separate(replicas[k], mix_d, shifts_host[lo:hi].to(ddev, non_blocking=True), Strict,
+                                                 save_input, part, saved)
+                        done = torch.cuda.Event()
+                        done.record(torch.cuda.current_stream(ddev))
+                        parts.append((lo, hi, part, done, d))
+                for lo, hi, part, done, d in parts:
+                    if d != dev.index:
+                        torch.cuda.current_stream(dev).wait_event(done)
+                        results[lo:hi].copy_(part, non_blocking=True)
         return results, (torch.cat(saved) if saved else torch.zeros((0, M, T)))
 
     def shift_and_sep(self, input_channels, patch_list, Strict=0, save_input=False):

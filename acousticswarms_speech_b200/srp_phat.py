@@ -287,24 +287,65 @@ class SRP_PHAT(object):
         sig = signal.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
         res = self.native.score(sig, window)[0]
         self.SRP_map = torch.maximum(self.SRP_map, res)
-        self._map_host = self.SRP_map.cpu().numpy()
-        self.MAX_POWER = float(self._map_host.max())
-        self.Min_POWER = float(self._map_host.min())
-        self.fill_powermap_torch()
+        # MAX_POWER / Min_POWER / POWER_MAP (:347-357, :432-433) are host-side views of the map: materialised on first
+        # access.  Apply_SRP_PHAT prunes on the device and never reads them, so the drop-in call no longer pays a
+        # blocking copy of the map plus the 1e5-voxel scatter per mixture.
+        self._host_stale = True
 
     def load_map(self, srp_map):
         """Install an externally computed map (G,) as if SRP_Map_WINDOW_new had produced it
         (used by the batched front end, which scores many mixtures in one launch, and by tests)."""
-        self._map_host = np.asarray(srp_map)
-        self.SRP_map = torch.from_numpy(np.ascontiguousarray(self._map_host))
-        self.MAX_POWER = float(self._map_host.max())
-        self.Min_POWER = float(self._map_host.min())
-        self.fill_powermap_torch()
+        self.SRP_map = torch.from_numpy(np.ascontiguousarray(np.asarray(srp_map)))
+        self._host_stale = True
+
+    def _sync_host(self):
+        """Bring the host-side views of the current map up to date (no-op when they are)."""
+        if getattr(self, "_host_stale", False):
+            self._host_stale = False
+            m = self.SRP_map.detach().cpu().numpy()
+            self._map_host_v = m
+            self._max_power = float(m.max())
+            self._min_power = float(m.min())
+            self._power_map[self._member] = m[self.POWER_INDEX[self._member]]       # fill_powermap (:347-357) as one gather
 
     def fill_powermap_torch(self):
-        """:347-357 as one gather."""
-        m = self._map_host if hasattr(self, "_map_host") else self.SRP_map.cpu().numpy()
-        self.POWER_MAP[self._member] = m[self.POWER_INDEX[self._member]]
+        """:347-357: POWER_MAP from the current map (kept for callers of the reference's method; the properties below
+        do the same on demand)."""
+        self._host_stale = True
+        self._sync_host()
+
+    @property
+    def _map_host(self):
+        self._sync_host()
+        v = getattr(self, "_map_host_v", None)
+        return v if v is not None else self.SRP_map.detach().cpu().numpy()
+
+    @property
+    def MAX_POWER(self):
+        self._sync_host()
+        return self._max_power
+
+    @MAX_POWER.setter
+    def MAX_POWER(self, v):
+        self._max_power = v
+
+    @property
+    def Min_POWER(self):
+        self._sync_host()
+        return self._min_power
+
+    @Min_POWER.setter
+    def Min_POWER(self, v):
+        self._min_power = v
+
+    @property
+    def POWER_MAP(self):
+        self._sync_host()
+        return self._power_map
+
+    @POWER_MAP.setter
+    def POWER_MAP(self, v):
+        self._power_map = v
 
     # ---- pruning -----------------------------------------------------------------------------
     def find_valid_peak_new(self, rato=SRP_THRESHOLD_RATIO):
@@ -391,8 +432,7 @@ class SRP_PHAT(object):
             self.peak_candidate = np.zeros((0, 3))
             return []
         if peak_values is None:
-            m = self._map_host if hasattr(self, "_map_host") else self.SRP_map.cpu().numpy()
-            peaks = m[peak_index]
+            peaks = self._map_host[peak_index]
         else:
             peaks = np.asarray(peak_values)
         peaks_pos = self.grids[peak_index]

@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--unique-batches", type=int, default=4, help="distinct resident sub-batches the step cycles through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip", default="", help="comma list of sub-benchmarks to skip: c1,c3,c5,sharded,e2e,variants")
+    ap.add_argument("--c3-group", type=int, default=16, help="mixtures per group of the c3 fine-stage pipeline")
     ap.add_argument("--count-sync", type=int, default=1,
                     help="1: the host reads each sub-batch's patch count (4 bytes, behind the pruning of the NEXT "
                          "sub-batch's scoring) and launches exactly the patches selected; 0: capacity-sized counted "
@@ -746,7 +747,7 @@ def bench_c3(args, fe, node, mix_devs, dev, pk, reduce_max, barrier, world):
     patch count per group, behind the previous group's stacking."""
     import torch
     from acousticswarms_speech_b200 import native
-    GB, NMIX = 16, 64
+    GB, NMIX = args.c3_group, 64
     B, M, T = mix_devs[0].shape
     groups = []
     for x in mix_devs:
@@ -842,7 +843,8 @@ def bench_c3(args, fe, node, mix_devs, dev, pk, reduce_max, barrier, world):
     assert (sh0[:, 0] == 0).all() and mi0.min() >= 0 and mi0.max() < GB and (np.diff(mi0) >= 0).all()
     return {"workload": "C3: fine width-2 Spotform_Small_Patch_Parallel refinement over surviving hypercubes, 64 mixtures per GPU, "
                         "7 mics, 3 s @ 48 kHz", "mixtures_per_gpu": NMIX, "fine_patches_per_gpu": total,
-            "fine_patches_per_mixture": total / NMIX, "ms_per_pass": ms, "corr_table_max_lag": max_lag, "patches_per_s": world * total / (ms / 1e3),
+            "fine_patches_per_mixture": total / NMIX, "ms_per_pass": ms, "corr_table_max_lag": max_lag,
+            "mixtures_per_group": GB, "patches_per_s": world * total / (ms / 1e3),
             "hbm": {"algorithmic_bytes": byts, "achieved_gbs": byts / (ms / 1e3) / 1e9,
                     "frac": byts / (ms / 1e3) / 1e9 / pk["hbm_gbs"],
                     "kernel_avg_launch_ms": k_ms, "kernel_achieved_gbs": 4.0 * fe.net_batch * M * T / (k_ms / 1e3) / 1e9,

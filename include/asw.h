@@ -19,6 +19,13 @@
  *     ASW_ERR_CUDA.
  *   - a handle is not thread-safe (the reference is single-threaded per
  *     Mic_Array); use one handle per device / per host thread.
+ *   - a handle is SINGLE-STREAM and not re-entrant: every handle (asw_srp_t,
+ *     asw_peaks_t, asw_select_t, asw_corr_t) owns one workspace that each call
+ *     reuses whatever stream it is given.  Two calls on the same handle must
+ *     be ordered by the caller (same stream, or an event between the streams);
+ *     calls on different handles are independent.
+ *   - shift tables: a row whose mixture index is outside [0, B) is skipped by
+ *     every shift-stack entry point (never read out of bounds).
  */
 #ifndef ASW_H_
 #define ASW_H_

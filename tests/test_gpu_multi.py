@@ -55,3 +55,49 @@ def test_two_devices_in_one_process(cuda_device):
         assert torch.cuda.current_device() == 0
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+def test_patch_sharded_spot_model_two_gpus(cuda_device):
+    """DataParallelSpotModel over two devices: the patch list is sharded (each device stacks and normalises its slice
+    next to its replica of the network) instead of nn.DataParallel scattering the stacked batch
+    (sep/training/JointModel/network.py:30).  Outputs must equal the single-device path: bit for bit for a network
+    that is pure arithmetic on the normalised stack, to float32 round-off for a convolutional one (replicated
+    weights)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    import numpy as np
+    from acousticswarms_speech_b200.spot import DataParallelSpotModel
+    from oracle import prune_oracle
+
+    class MeanNet(torch.nn.Module):
+        def forward(self, x, cond):
+            return x.mean(1, keepdim=True) * (cond[:, 1:2] + 2 * cond[:, 0:1]).unsqueeze(-1)
+
+    class ConvNet(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.c = torch.nn.Conv1d(m, 1, 9, padding=4)
+
+        def forward(self, x, cond):
+            return self.c(x) * (cond[:, 1:2] + 2 * cond[:, 0:1]).unsqueeze(-1)
+
+    rng = np.random.default_rng(3)
+    M, T, N = 7, 48000, 301
+    mix = torch.from_numpy((0.05 * rng.standard_normal((M, T))).astype(np.float32))
+    patches = [prune_oracle.Patch(rng.integers(-200, 201, size=M - 1).astype(np.int64), np.full(M - 1, 4), None) for _ in range(N)]
+    torch.manual_seed(0)
+    for net, exact in ((MeanNet(), True), (ConvNet(M), False)):
+        single = DataParallelSpotModel(net, batch_size=64, data_parallel=False)
+        multi = DataParallelSpotModel(net, batch_size=64, device_ids=[0, 1])
+        assert multi.device_ids == [0, 1] and single.device_ids == [0]
+        for strict in (0, 1):
+            a = single.shift_and_sep(mix, patches, Strict=strict)
+            b = multi.shift_and_sep(mix, patches, Strict=strict)
+            assert a.shape == b.shape == (N, T)
+            if exact:
+                assert np.array_equal(a, b)
+            else:
+                assert np.abs(a - b).max() <= 1e-5 * np.abs(a).max()
+        rows = multi.shift_and_sep_device(mix, patches[:130], Strict=1)
+        assert rows.shape == (130, T) and rows.x.device.index == 0
+    assert torch.cuda.current_device() == 0
