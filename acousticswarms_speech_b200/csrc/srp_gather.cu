@@ -12,6 +12,9 @@
 // per-window sums stay in registers; the max over windows is taken at the end.  Hypercubes are visited in the k-d
 // order built by asw_srp_create (a warp's 32 hypercubes are neighbours in every pair's table), results are written
 // back through the slot -> hypercube permutation.  The kernel is shared-memory-bandwidth bound (16 B per gather).
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace asw {
@@ -127,6 +130,197 @@ __global__ void __launch_bounds__(kThreads, kMaxThreads / kThreads) srp_gather_k
     }
 }
 
+// ---- round 2: persistent CTAs, bulk-copy (TMA) staging, mbarrier pipeline ----------------------------------------------
+// The staged rows are contiguous, 16-byte aligned 1-D ranges -- the one place on this path where "TMA where tiles are
+// regular" applies.  One CTA per SM walks a flat sequence of stages (tile, window chunk, pair group) through the same
+// two shared-memory buffers:
+//   * warp 0 issues one cp.async.bulk per (pair, window) row of the NEXT stage (a lane per row) and arms the stage's
+//     `full` mbarrier with the byte count; nobody executes per-lane copy instructions or waits for "its" copies;
+//   * every warp waits on `full`, gathers, and arrives on the stage's `empty` mbarrier; only the issuing warp ever
+//     waits on `empty`, so there is no block-wide barrier in the loop and fast warps run ahead into the next stage;
+//   * because the sequence continues across tiles, the first fill of a tile overlaps the last gathers of the previous
+//     one (the first version paid that latency once per CTA, twice per SM at the C2 size).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct StageCursor {      // position in a CTA's flat stage sequence
+    int item, w0, grp;
+};
+
+template <int GPT, int kThreads>
+__global__ void __launch_bounds__(kThreads, 1) srp_gather_bulk_kernel(SrpGatherParams p, int ntiles, int n_items) {
+    extern __shared__ __align__(128) float s_tab[];
+    __shared__ uint64_t s_full[2], s_empty[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kThreads / 32;
+    if (tid == 0) {
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        mbar_init(&s_empty[0], kWarps);
+        mbar_init(&s_empty[1], kWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto groups_of = [&](int item) { const int t = item % ntiles; return p.tile_grp[t + 1] - p.tile_grp[t] - 1; };
+    auto advance = [&](StageCursor c) {      // next stage of this CTA; item >= n_items: past the end
+        if (c.grp + 1 < groups_of(c.item)) {
+            ++c.grp;
+        } else if (c.w0 + kWc < p.Nw) {
+            c.w0 += kWc;
+            c.grp = 0;
+        } else {
+            c.item += gridDim.x;
+            c.w0 = 0;
+            c.grp = 0;
+        }
+        return c;
+    };
+    // warp 0: one bulk copy per (pair, window) row of the stage, a lane per row; lane 0 arms the barrier
+    auto issue = [&](StageCursor c, int bufi) {
+        const int b = c.item / ntiles, t = c.item % ntiles;
+        const float* gcc_b = p.gcc + (size_t)b * p.tab_len * p.Nw;
+        const int* rlo = p.rng_lo + (size_t)t * p.P;
+        const int* rn = p.rng_n + (size_t)t * p.P;
+        const int* gb = p.grp_flat + p.tile_grp[t];
+        const int wc = min(kWc, p.Nw - c.w0);
+        float* buf = s_tab + bufi * p.stage_floats;
+        int so = 0, row = 0;
+        for (int pp = gb[c.grp]; pp < gb[c.grp + 1]; ++pp) {
+            const int npd = p.npad[pp], n = rn[pp], lo = rlo[pp];
+            const float* src = gcc_b + (size_t)p.Nw * p.off[pp] + (size_t)c.w0 * npd + lo;
+            for (int w = 0; w < wc; ++w, ++row)
+                if ((row & 31) == lane) bulk_load(buf + so + w * n, src + (size_t)w * npd, (uint32_t)n * 4u, &s_full[bufi]);
+            so += wc * n;
+        }
+        if (lane == 0) mbar_expect_tx(&s_full[bufi], (uint32_t)so * 4u);
+    };
+
+    StageCursor cur{(int)blockIdx.x, 0, 0};
+    if (cur.item >= n_items) return;
+    if (warp == 0) issue(cur, 0);
+
+    bool on[GPT];
+    float best[GPT];
+    float acc[kWc][GPT];
+    int s = 0;
+    while (cur.item < n_items) {
+        const StageCursor nxt = advance(cur);
+        const int bufi = s & 1;
+        if (warp == 0 && nxt.item < n_items) {
+            // the other buffer was last read by stage s - 1: every warp has arrived on its `empty` barrier before the refill
+            if (s >= 1) mbar_wait(&s_empty[bufi ^ 1], (uint32_t)(((s - 1) >> 1) & 1));
+            issue(nxt, bufi ^ 1);
+        }
+        const int b = cur.item / ntiles, t = cur.item % ntiles;
+        const int g_base = t * p.tile;
+        const int* rlo = p.rng_lo + (size_t)t * p.P;
+        const int* rn = p.rng_n + (size_t)t * p.P;
+        const int* gb = p.grp_flat + p.tile_grp[t];
+        const int n_groups = p.tile_grp[t + 1] - p.tile_grp[t] - 1;
+        const int wc = min(kWc, p.Nw - cur.w0);
+        if (cur.grp == 0) {
+            if (cur.w0 == 0) {
+#pragma unroll
+                for (int gi = 0; gi < GPT; ++gi) {
+                    const int sl = gi * kThreads + tid;
+                    on[gi] = sl < p.tile && g_base + sl < p.G;
+                    best[gi] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < kWc; ++w)
+#pragma unroll
+                for (int gi = 0; gi < GPT; ++gi) acc[w][gi] = 0.f;
+        }
+        const float* s_cur = s_tab + bufi * p.stage_floats;
+        mbar_wait(&s_full[bufi], (uint32_t)((s >> 1) & 1));
+        int sm_off = 0;
+        for (int pp = gb[cur.grp]; pp < gb[cur.grp + 1]; ++pp) {
+            const int n = rn[pp], lo = rlo[pp];
+#pragma unroll
+            for (int gi = 0; gi < GPT; ++gi) {
+                if (!on[gi]) continue;
+                const uint32_t q = __ldg(p.pos + (size_t)pp * p.Gpad + g_base + gi * kThreads + tid);
+                const int i0 = (int)(q >> kFracBits);
+                const float f = (float)(q & ((1u << kFracBits) - 1)) * (1.0f / (float)(1 << kFracBits));
+                // 4-tap Lagrange weights for nodes -1, 0, 1, 2 (same expressions as srp_gather_kernel: same bits)
+                const float fm1 = f - 1.f, fm2 = f - 2.f, fp1 = f + 1.f;
+                const float c0 = -(1.f / 6.f) * f * fm1 * fm2;
+                const float c1 = 0.5f * fp1 * fm1 * fm2;
+                const float c2 = -0.5f * fp1 * f * fm2;
+                const float c3 = (1.f / 6.f) * fp1 * f * fm1;
+                const float* tp = s_cur + sm_off + (i0 - lo) - 1;
+#pragma unroll
+                for (int w = 0; w < kWc; ++w) {
+                    if (w < wc) {
+                        float v = c0 * tp[0];
+                        v = fmaf(c1, tp[1], v);
+                        v = fmaf(c2, tp[2], v);
+                        v = fmaf(c3, tp[3], v);
+                        acc[w][gi] += v;
+                        tp += n;
+                    }
+                }
+            }
+            sm_off += wc * n;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[bufi]);              // this warp is done reading the stage
+        if (cur.grp == n_groups - 1) {
+#pragma unroll
+            for (int w = 0; w < kWc; ++w)
+                if (w < wc) {
+#pragma unroll
+                    for (int gi = 0; gi < GPT; ++gi) best[gi] = fmaxf(best[gi], acc[w][gi]);
+                }
+            if (cur.w0 + kWc >= p.Nw) {
+#pragma unroll
+                for (int gi = 0; gi < GPT; ++gi) {
+                    const int slot = g_base + gi * kThreads + tid;
+                    if (on[gi]) p.map[(size_t)b * p.G + p.perm[slot]] = best[gi];
+                }
+            }
+        }
+        cur = nxt;
+        ++s;
+    }
+}
+
+template <int GPT, int kThreads>
+int launch_bulk_t(const SrpGatherParams& p, cudaStream_t s) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(srp_gather_bulk_kernel<GPT, kThreads>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kSmemBudget));
+    }
+    const int ntiles = (p.G + p.tile - 1) / p.tile;
+    const long long items = (long long)ntiles * p.B;
+    const int grid = (int)(items < kNumSms ? items : kNumSms);
+    srp_gather_bulk_kernel<GPT, kThreads><<<grid, kThreads, 2 * (size_t)p.stage_floats * sizeof(float), s>>>(p, ntiles, (int)items);
+    ASW_LAUNCH_CHECK("srp_gather_bulk_kernel");
+    return ASW_OK;
+}
+
 template <int GPT, int kThreads>
 int launch_t(const SrpGatherParams& p, cudaStream_t s) {
     static PerDeviceOnce attr_once;
@@ -181,9 +375,16 @@ int launch_srp_gather(const SrpGatherParams& p, cudaStream_t s) {
         set_error("srp_gather: stage of %zu bytes exceeds the shared-memory budget", (size_t)p.stage_floats * sizeof(float));
         return ASW_ERR_RANGE;
     }
-    if (p.tile > 2 * kMaxThreads) return launch_t<3, kThreads3>(p, s);
-    if (p.tile > kMaxThreads) return launch_t<2, kMaxThreads>(p, s);
-    return launch_t<1, kMaxThreads>(p, s);
+    // ASW_GATHER=legacy: the round-1 kernel (per-lane cp.async ring, one CTA per tile), kept for A/B measurements
+    static const bool legacy = [] { const char* e = getenv("ASW_GATHER"); return e && strcmp(e, "legacy") == 0; }();
+    if (legacy) {
+        if (p.tile > 2 * kMaxThreads) return launch_t<3, kThreads3>(p, s);
+        if (p.tile > kMaxThreads) return launch_t<2, kMaxThreads>(p, s);
+        return launch_t<1, kMaxThreads>(p, s);
+    }
+    if (p.tile > 2 * kMaxThreads) return launch_bulk_t<3, kThreads3>(p, s);
+    if (p.tile > kMaxThreads) return launch_bulk_t<2, kMaxThreads>(p, s);
+    return launch_bulk_t<1, kMaxThreads>(p, s);
 }
 
 }  // namespace asw

@@ -16,13 +16,18 @@ from .constants import SPOT_BATCH_SIZE, window_length
 
 
 class FrontEnd:
-    def __init__(self, srp_node, device=None, net_batch=SPOT_BATCH_SIZE, ring=2, topk=128):
-        """``srp_node``: an ``acousticswarms_speech_b200.srp_phat.SRP_PHAT`` (geometry + device handle)."""
+    def __init__(self, srp_node, device=None, net_batch=SPOT_BATCH_SIZE, ring=2, topk=128, launch_batches=1):
+        """``srp_node``: an ``acousticswarms_speech_b200.srp_phat.SRP_PHAT`` (geometry + device handle).
+        ``ring``: how many (net_batch, M, T) network-input buffers are cycled through; ``launch_batches``: how many
+        of them one shift-stack launch fills (the reference fills one 128-patch buffer at a time,
+        sep/training/JointModel/network.py:58; with 180 GB of HBM a deeper ring lets one launch stack several network
+        batches ahead of the consumer and saves the launch gaps)."""
         self.node = srp_node
         self.h = srp_node.native
         self.device = srp_node.device if device is None else torch.device(device)
         self.net_batch = net_batch
-        self.ring = ring
+        self.ring = max(ring, launch_batches)
+        self.launch_batches = max(1, launch_batches)
         self.topk = topk
         self._bufs = None
         self._map = None
@@ -42,9 +47,11 @@ class FrontEnd:
 
     # ---- shift-stack -----------------------------------------------------------------------------
     def _ring(self, M, T):
-        if self._bufs is None or self._bufs[0].shape != (self.net_batch, M, T):
-            self._bufs = [torch.empty((self.net_batch, M, T), device=self.device, dtype=torch.float32)
-                          for _ in range(self.ring)]
+        """The ring as ``ring // launch_batches`` contiguous segments of ``launch_batches`` network batches each."""
+        rows = self.net_batch * self.launch_batches
+        if self._bufs is None or self._bufs[0].shape != (rows, M, T):
+            self._bufs = [torch.empty((rows, M, T), device=self.device, dtype=torch.float32)
+                          for _ in range(max(1, self.ring // self.launch_batches))]
         return self._bufs
 
     def stack(self, mix_dev, shifts_dev, mix_index_dev, consumer=None, fused_norm=False, events=None):
@@ -57,7 +64,7 @@ class FrontEnd:
         launches = 0
         for k, i in enumerate(range(0, N, self.net_batch)):
             n = min(self.net_batch, N - i)
-            buf = bufs[k % self.ring]
+            buf = bufs[k % len(bufs)][:self.net_batch]
             if events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -116,9 +123,10 @@ class FrontEnd:
         rows beyond n_total are skipped on the device."""
         B, M, T = mix_dev.shape
         bufs = self._ring(M, T)
-        for k, i in enumerate(range(0, capacity, self.net_batch)):
-            n = min(self.net_batch, capacity - i)
-            buf = bufs[k % self.ring]
+        rows = self.net_batch * self.launch_batches
+        for k, i in enumerate(range(0, capacity, rows)):
+            n = min(rows, capacity - i)
+            buf = bufs[k % len(bufs)]
             if events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -158,9 +166,10 @@ class FrontEnd:
         launch into the ring; rows >= n_total[0] are skipped on the device.  ``tables``: CorrTables.compute(mix_dev)."""
         B, M, T = mix_dev.shape
         bufs = self._ring(M, T)
-        for k, i in enumerate(range(0, n_rows, self.net_batch)):
-            n = min(self.net_batch, n_rows - i)
-            buf = bufs[k % self.ring]
+        rows = self.net_batch * self.launch_batches
+        for k, i in enumerate(range(0, n_rows, rows)):
+            n = min(rows, n_rows - i)
+            buf = bufs[k % len(bufs)]
             if events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()

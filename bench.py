@@ -5,14 +5,14 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 The headline workload is config C2 of SURVEY.md section 8d (7 mics, 5 speakers, 3 s @ 48 kHz, one desk geometry,
-G ~ 2e4 hypercubes).  One STEP = S sub-batches of B synthetic mixtures per GPU (default 24 x 32 = 768 mixtures, so
+G ~ 2e4 hypercubes).  One STEP = S sub-batches of B synthetic mixtures per GPU (default 12 x 64 = 768 mixtures, so
 the timed region lasts ~0.5 s); every sub-batch runs the complete device path
     asw_srp_score (STFT+PHAT+cross-spectra -> GCC lag tables -> SRP gather, max over windows)
     asw_map_topk  (MAX_POWER and the K best hypercubes per mixture)
     asw_peaks_find (fill_powermap + find_valid_peak_new: thresholded 3-D local maxima -> peak hypercubes)
     asw_select_patches + asw_build_shift_table (local_source_adaptive -> dense per-sub-batch patch table)
-    asw_shift_stack of every coarse hypercube patch of every mixture, 128 patches per launch into a ring of
-                  (128, M, T) network-input buffers
+    asw_shift_stack of every coarse hypercube patch of every mixture into a ring of (128, M, T) network-input
+                  buffers, 9 of them (1152 patches) per launch
 with scoring / pruning / stacking of consecutive sub-batches software-pipelined on three streams.  Every sub-batch
 selects its own patches on the device.  `value` starts with inputs resident in HBM; `e2e` starts from pinned host
 buffers (16-bit PCM, what the data is) and ends with the maps / top-K / patch lists back on the host.
@@ -53,11 +53,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="mixtures per GPU per sub-batch")
-    ap.add_argument("--sub-batches", type=int, default=24, help="sub-batches per step (a step = sub-batches x batch mixtures)")
+    ap.add_argument("--batch", type=int, default=64, help="mixtures per GPU per sub-batch")
+    ap.add_argument("--sub-batches", type=int, default=12, help="sub-batches per step (a step = sub-batches x batch mixtures)")
     ap.add_argument("--unique-batches", type=int, default=4, help="distinct resident sub-batches the step cycles through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip", default="", help="comma list of sub-benchmarks to skip: c1,c3,c5,sharded,e2e,variants")
+    ap.add_argument("--launch-batches", type=int, default=9,
+                    help="128-patch network batches stacked by one shift-stack launch (ring of that many buffers)")
     ap.add_argument("--c3-group", type=int, default=16, help="mixtures per group of the c3 fine-stage pipeline")
     ap.add_argument("--count-sync", type=int, default=1,
                     help="1: the host reads each sub-batch's patch count (4 bytes, behind the pruning of the NEXT "
@@ -313,6 +315,12 @@ class C2Pipeline:
                 self.ntot_pin[slot].copy_(ntot_dev, non_blocking=True)
             if self.mode == "norm":
                 self.corr.compute(src, out=self.corr_tabs[slot])
+            # the shift-stack (and the host's count read) wait for the table only, not for the result copies below
+            pruned = torch.cuda.Event()
+            pruned.record(pstream)
+            if timing_stages:
+                self.stage_events[-1][2].record(pstream)
+            self.map_free[slot] = pruned
             if to_host:
                 sp = self.sel_pin
                 sp[:, 0].copy_(n_p, non_blocking=True)
@@ -324,11 +332,8 @@ class C2Pipeline:
                 self.map_pin.copy_(m, non_blocking=True)
                 self.val_pin.copy_(val, non_blocking=True)
                 self.idx_pin.copy_(idx, non_blocking=True)
-            pruned = torch.cuda.Event()
-            pruned.record(pstream)
-            if timing_stages:
-                self.stage_events[-1][2].record(pstream)
-            self.map_free[slot] = pruned
+                self.map_free[slot] = torch.cuda.Event()      # the map buffer is free once it has been copied out
+                self.map_free[slot].record(pstream)
             for t in (peaks, count, n_p, off_p, wid_p, pk_p):
                 t.record_stream(pstream)
         n_rows = self.cap
@@ -396,7 +401,7 @@ def run_b200(args, rank, world):
     node = SRP_PHAT(scene.mic_positions, freq_bins, scene.roi, FS=FS, n_fft=n_fft, grid_size=0.05,
                     threshold=list(SRP_THRESHOLDS), WIDTH=8, device=dev)
     node.native.set_stft_path(args.stft_path)
-    fe = FrontEnd(node, dev)
+    fe = FrontEnd(node, dev, launch_batches=args.launch_batches, ring=2 * args.launch_batches)
     G = node.grids.shape[0]
     M, T = N_MICS, T_SAMPLES
 
@@ -446,7 +451,7 @@ def run_b200(args, rank, world):
     # e2e: every sub-batch copies its B mixtures from pinned host memory (ring of NBUF device buffers on a copy stream,
     # so the PCIe transfer of sub-batch i+1 overlaps the kernels of sub-batch i) and returns maps, top-K, peaks and
     # patch lists to the host.
-    copy_stream = torch.cuda.Stream(device=dev)
+    copy_stream = torch.cuda.Stream(device=dev, priority=-1)     # the PCM expansion kernel must not queue behind the stack
     NBUF = 3
     in_bufs = [torch.empty_like(mix_devs[0]) for _ in range(NBUF)]
     pcm_bufs = [torch.empty((B, M, T), device=dev, dtype=torch.int16) for _ in range(NBUF)]
@@ -541,25 +546,28 @@ def run_b200(args, rank, world):
         torch.cuda.synchronize()
         pipe.serial = saved[0]
         k = [(a.elapsed_time(b), n) for a, b, n in events]
-        if pipe.count_sync:
-            full = [t for t, n in k if n == fe.net_batch]
-        else:       # capacity-sized launches: only those whose 128 rows all lie below the sub-batch's patch count
-            per = (cap + fe.net_batch - 1) // fe.net_batch
-            full = [t for i, (t, n) in enumerate(k) if ((i % per) + 1) * fe.net_batch <= n_per[((i // per) % NSUB) % NU]]
+        rows_full = fe.net_batch * fe.launch_batches
+        if pipe.count_sync:     # every launch covers exactly the rows it was given: use those of at least one network batch
+            sel = [(t, n) for t, n in k if n >= fe.net_batch]
+        else:       # capacity-sized launches: only those whose rows all lie below the sub-batch's patch count
+            per = (cap + rows_full - 1) // rows_full
+            sel = [(t, n) for i, (t, n) in enumerate(k) if ((i % per) + 1) * rows_full <= n_per[((i // per) % NSUB) % NU]]
         st = pipe.stage_events[1:] or pipe.stage_events
-        out = {"avg_launch_ms": sum(full) / max(1, len(full)), "full_launches_timed": len(full),
+        rows = sum(n for _, n in sel)
+        out = {"avg_launch_ms": sum(t for t, _ in sel) / max(1, len(sel)), "full_launches_timed": len(sel),
+               "rows_per_launch": rows / max(1, len(sel)), "ms_per_128_rows": sum(t for t, _ in sel) / max(1, rows) * 128,
                "score_ms": sum(e[0].elapsed_time(e[1]) for e in st) / len(st),
                "prune_ms": sum(e[1].elapsed_time(e[2]) for e in st) / len(st),
                "stack_ms": sum(e[2].elapsed_time(e[3]) for e in st) / len(st)}
         pipe.mode = "plain"
         return out
 
-    launch_bytes = 4.0 * fe.net_batch * M * T
-
     def variant(kp, kernel):
-        a = launch_bytes / (kp["avg_launch_ms"] / 1e3) / 1e9
+        byts = 4.0 * kp["rows_per_launch"] * M * T
+        a = byts / (kp["avg_launch_ms"] / 1e3) / 1e9
         return {"kernel": kernel, "achieved": a, "frac": a / pk["hbm_gbs"], "avg_launch_ms": kp["avg_launch_ms"],
-                "launches_timed": kp["full_launches_timed"]}
+                "algorithmic_bytes_per_launch": byts, "patches_per_launch": kp["rows_per_launch"],
+                "ms_per_128_patches": kp["ms_per_128_rows"], "launches_timed": kp["full_launches_timed"]}
 
     kp_plain = kernel_pass("plain")
     variants = {"plain": variant(kp_plain, "shift_stack_vec_kernel<false>")}
@@ -589,6 +597,8 @@ def run_b200(args, rank, world):
         out = []
         for j in range(2):                                            # both buffer slots
             slot = pipe.step_no & 1
+            for bf in fe._bufs:                                       # rows no launch of this sub-batch writes: zeros
+                bf.zero_()
             pipe.compute(mix_devs[j % NU], to_host=True)
             pipe.join()
             torch.cuda.synchronize()
@@ -663,7 +673,7 @@ def run_b200(args, rank, world):
         "config": {"workload": WORKLOAD, "mixtures_per_gpu_per_step": NSUB * B, "sub_batches_per_step": NSUB,
                    "mixtures_per_sub_batch": B, "distinct_resident_sub_batches": NU, "hypercubes": G, "mics": M,
                    "speakers": N_SPK, "samples": T, "fs": FS, "coarse_patches_per_step_per_gpu": patches_per_step,
-                   "net_batch": fe.net_batch, "streams": args.streams, "count_sync": int(pipe.count_sync),
+                   "net_batch": fe.net_batch, "network_batches_per_stack_launch": fe.launch_batches, "streams": args.streams, "count_sync": int(pipe.count_sync),
                    "parallelism": f"mixtures sharded over {world} GPU(s)",
                    "l2": f"every sub-batch reads {B * M * T * 4 / 1e6:.0f} MB of inputs it last touched {NU} sub-batches "
                          f"({NU * B * M * T * 4 / 1e6:.0f} MB) ago and writes {n_per[0] * M * T * 4 / 1e9:.2f} GB of stacked "
@@ -677,7 +687,8 @@ def run_b200(args, rank, world):
         "gpu_launches": int(launches), "host_issue_ms_per_step": host_ms,
         "roofline": {"kernel": "shift_stack_vec_kernel", "bound": "hbm", "achieved": variants["plain"]["achieved"],
                      "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": variants["plain"]["frac"],
-                     "peak_kind": pk_kind + " (copy, burst)", "algorithmic_bytes_per_launch": launch_bytes,
+                     "peak_kind": pk_kind + " (copy, burst)",
+                     "algorithmic_bytes_per_launch": variants["plain"]["algorithmic_bytes_per_launch"],
                      "avg_launch_ms": variants["plain"]["avg_launch_ms"], "traffic": None,
                      "variants": variants,
                      "step": {"algorithmic_bytes_per_step": stack_bytes + score_bytes,
@@ -761,7 +772,7 @@ def bench_c3(args, fe, node, mix_devs, dev, pk, reduce_max, barrier, world):
     max_lag = native.CorrTables.lag_for_geometry(node.mic_pos, node.FS)
     corr = native.CorrTables(M, dev, max_lag=max_lag)
     front_stream, stack_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    fe_fine = type(fe)(node, dev, net_batch=fe.net_batch, ring=2)      # its own ring and map buffers
+    fe_fine = type(fe)(node, dev, net_batch=fe.net_batch, launch_batches=8, ring=16)    # its own ring and map buffers
 
     def front(x):
         """Everything before the stack, on the front stream; returns the device tables + an event."""
@@ -830,8 +841,9 @@ def bench_c3(args, fe, node, mix_devs, dev, pk, reduce_max, barrier, world):
     t1.record()
     torch.cuda.synchronize()
     ms_serial = t0.elapsed_time(t1)
-    k = [a.elapsed_time(b) for a, b, n in events if n == fe.net_batch]
-    k_ms = sum(k) / max(1, len(k))
+    k = [(a.elapsed_time(b), n) for a, b, n in events if n >= fe.net_batch]
+    k_rows = sum(n for _, n in k)
+    k_ms = sum(t for t, _ in k) / max(1, k_rows) * fe.net_batch          # per 128 patches
     stack_ms = sum(a.elapsed_time(b) for a, b, n in events)
     byts = 4.0 * total * M * T
     # spot check of the device-built fine table against the reference's host loop on one candidate-rich mixture is
@@ -847,9 +859,10 @@ def bench_c3(args, fe, node, mix_devs, dev, pk, reduce_max, barrier, world):
             "mixtures_per_group": GB, "patches_per_s": world * total / (ms / 1e3),
             "hbm": {"algorithmic_bytes": byts, "achieved_gbs": byts / (ms / 1e3) / 1e9,
                     "frac": byts / (ms / 1e3) / 1e9 / pk["hbm_gbs"],
-                    "kernel_avg_launch_ms": k_ms, "kernel_achieved_gbs": 4.0 * fe.net_batch * M * T / (k_ms / 1e3) / 1e9,
+                    "kernel_ms_per_128_patches": k_ms, "patches_per_launch": fe_fine.net_batch * fe_fine.launch_batches,
+                    "kernel_achieved_gbs": 4.0 * fe.net_batch * M * T / (k_ms / 1e3) / 1e9,
                     "kernel_frac": 4.0 * fe.net_batch * M * T / (k_ms / 1e3) / 1e9 / pk["hbm_gbs"],
-                    "kernel": "shift_ref_stats_kernel (table look-ups) + shift_stack_vec_kernel<true>, 128 patches per launch"},
+                    "kernel": "shift_ref_stats_kernel (table look-ups) + shift_stack_vec_kernel<true>"},
             "serial_pass_ms": ms_serial, "serial_stack_ms": stack_ms, "serial_front_ms": ms_serial - stack_ms,
             "note": "timed pass = score + peaks + selection + asw_subdivide + fine table + correlation tables + fused "
                     "shift-stack/normalize of all fine patches, two groups in flight (front of group g+1 overlaps the "
