@@ -253,14 +253,28 @@ __global__ void __launch_bounds__(kThreads, 1) srp_gather_bulk_kernel(SrpGatherP
                 for (int gi = 0; gi < GPT; ++gi) acc[w][gi] = 0.f;
         }
         const float* s_cur = s_tab + bufi * p.stage_floats;
+        // the lag positions of the first pair are fetched before the wait for the stage, those of pair pp + 1 while
+        // pair pp is gathered: ncu showed the dependent global load at the head of every pair as the top stall
+        // (long_scoreboard 6.1 warps per issue) once the block barriers were gone
+        const int pp_end = gb[cur.grp + 1];
+        uint32_t qn[GPT];
+#pragma unroll
+        for (int gi = 0; gi < GPT; ++gi)
+            qn[gi] = on[gi] ? __ldg(p.pos + (size_t)gb[cur.grp] * p.Gpad + g_base + gi * kThreads + tid) : 0u;
         mbar_wait(&s_full[bufi], (uint32_t)((s >> 1) & 1));
         int sm_off = 0;
-        for (int pp = gb[cur.grp]; pp < gb[cur.grp + 1]; ++pp) {
+        for (int pp = gb[cur.grp]; pp < pp_end; ++pp) {
             const int n = rn[pp], lo = rlo[pp];
+            uint32_t qc[GPT];
+#pragma unroll
+            for (int gi = 0; gi < GPT; ++gi) {
+                qc[gi] = qn[gi];
+                if (pp + 1 < pp_end && on[gi]) qn[gi] = __ldg(p.pos + (size_t)(pp + 1) * p.Gpad + g_base + gi * kThreads + tid);
+            }
 #pragma unroll
             for (int gi = 0; gi < GPT; ++gi) {
                 if (!on[gi]) continue;
-                const uint32_t q = __ldg(p.pos + (size_t)pp * p.Gpad + g_base + gi * kThreads + tid);
+                const uint32_t q = qc[gi];
                 const int i0 = (int)(q >> kFracBits);
                 const float f = (float)(q & ((1u << kFracBits) - 1)) * (1.0f / (float)(1 << kFracBits));
                 // 4-tap Lagrange weights for nodes -1, 0, 1, 2 (same expressions as srp_gather_kernel: same bits)
