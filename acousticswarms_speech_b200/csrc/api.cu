@@ -259,7 +259,11 @@ int asw_srp_create(asw_srp_t** out, int device, int M, int G, const double* lag,
         set_error("asw_srp_create: oversample must be 1, 2, 4 or 8");
         return ASW_ERR_ARG;
     }
-    ASW_CUDA_CHECK(cudaSetDevice(device));
+    DeviceGuard guard(device);      // the caller's current device is restored on return
+    if (!guard.ok) {
+        set_error("cannot make device %d current", device);
+        return ASW_ERR_CUDA;
+    }
 
     asw_srp* h = new asw_srp();
     h->device = device;
@@ -397,7 +401,7 @@ int asw_srp_create(asw_srp_t** out, int device, int M, int G, const double* lag,
 
 int asw_srp_destroy(asw_srp_t* h) {
     if (!h) return ASW_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     cudaFree(h->d_lag_lo);
     cudaFree(h->d_n_entries);
     cudaFree(h->d_npad);

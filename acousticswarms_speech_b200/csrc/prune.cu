@@ -163,7 +163,11 @@ int asw_peaks_create(asw_peaks_t** out, int device, int Lx, int Ly, int Lz, int 
         return ASW_ERR_ARG;
     }
     *out = nullptr;
-    ASW_CUDA_CHECK(cudaSetDevice(device));
+    DeviceGuard guard(device);      // the caller's current device is restored on return
+    if (!guard.ok) {
+        set_error("cannot make device %d current", device);
+        return ASW_ERR_CUDA;
+    }
     asw_peaks* h = new asw_peaks();
     h->device = device;
     h->Lx = Lx;
@@ -199,7 +203,7 @@ int asw_peaks_create(asw_peaks_t** out, int device, int Lx, int Ly, int Lz, int 
 
 int asw_peaks_destroy(asw_peaks_t* h) {
     if (!h) return ASW_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     cudaFree(h->d_index);
     cudaFree(h->d_a1);
     cudaFree(h->d_a2);

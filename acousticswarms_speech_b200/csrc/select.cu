@@ -1221,7 +1221,11 @@ int asw_select_create(asw_select_t** out, int device, int G, int D, int W, const
         set_error("asw_select_create: 1 cm volume %d x %d x %d exceeds the packed index range (4095 x 4095 x 255)", Nx1, Ny1, Nz);
         return ASW_ERR_RANGE;
     }
-    ASW_CUDA_CHECK(cudaSetDevice(device));
+    DeviceGuard guard(device);      // the caller's current device is restored on return
+    if (!guard.ok) {
+        set_error("cannot make device %d current", device);
+        return ASW_ERR_CUDA;
+    }
     asw_select* h = new asw_select();
     h->device = device;
     h->G = G;
@@ -1301,7 +1305,7 @@ int asw_select_create(asw_select_t** out, int device, int G, int D, int W, const
 
 int asw_select_destroy(asw_select_t* h) {
     if (!h) return ASW_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     cudaFree(h->d_cl_off);
     cudaFree(h->d_off5);
     cudaFree(h->d_off1s);
@@ -1363,7 +1367,11 @@ int asw_select_set_grid1(asw_select_t* h, const double* xx1, const double* yy1, 
         set_error("asw_select_set_grid1: null argument");
         return ASW_ERR_ARG;
     }
-    ASW_CUDA_CHECK(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
+    if (!guard.ok) {
+        set_error("cannot make device %d current", h->device);
+        return ASW_ERR_CUDA;
+    }
     const size_t n = (size_t)h->Nx1 + h->Ny1 + h->Nz;
     if (!h->d_grid1) ASW_CUDA_CHECK(cudaMalloc(&h->d_grid1, n * sizeof(double)));
     ASW_CUDA_CHECK(cudaMemcpy(h->d_grid1, xx1, sizeof(double) * h->Nx1, cudaMemcpyHostToDevice));

@@ -354,7 +354,11 @@ int asw_corr_create(asw_corr_t** out, int device, int M, int max_lag) {
         set_error("asw_corr_create: M=%d (2..%d) / max_lag=%d (1..512) unsupported", M, kMaxMics, max_lag);
         return ASW_ERR_ARG;
     }
-    ASW_CUDA_CHECK(cudaSetDevice(device));
+    DeviceGuard guard(device);      // the caller's current device is restored on return
+    if (!guard.ok) {
+        set_error("cannot make device %d current", device);
+        return ASW_ERR_CUDA;
+    }
     asw_corr* h = new asw_corr();
     h->device = device;
     h->M = M;
@@ -382,7 +386,7 @@ int asw_corr_create(asw_corr_t** out, int device, int M, int max_lag) {
 
 int asw_corr_destroy(asw_corr_t* h) {
     if (!h) return ASW_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     cudaFree(h->d_tw1024);
     cudaFree(h->d_tw2048);
     cudaFree(h->d_spec);
