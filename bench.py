@@ -247,6 +247,7 @@ class C2Pipeline:
         self.max_lag = MAX_LAG
         self.stage_events = []
         self.launched_patches = []   # patches covered by every timed shift-stack launch (count-sync mode)
+        self.trace = None            # list of per-sub-batch event dicts while the pipelined schedule is being traced
 
     def enable_norm(self):
         from acousticswarms_speech_b200 import native
@@ -279,7 +280,14 @@ class C2Pipeline:
             st_ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             st_ev[0].record(main)
             self.stage_events.append(st_ev)
+        tr = None
+        if self.trace is not None and not self.serial:
+            tr = {k: torch.cuda.Event(enable_timing=True) for k in ("score0", "score1", "prune0", "prune1", "stack0", "stack1")}
+            self.trace.append(tr)
+            tr["score0"].record(main)
         m, val, idx = fe.score(src, out=self.maps[slot])
+        if tr:
+            tr["score1"].record(main)
         if self.collective:    # every rank learns every mixture's top-K
             ps = (self.step_no - 1) % self.NPACK
             pack = self.packs[ps]
@@ -308,6 +316,8 @@ class C2Pipeline:
             shifts_dev, mi_dev, ntot_dev = self.tables[slot]
             if self.table_free[slot] is not None:
                 pstream.wait_event(self.table_free[slot])     # stack of sub-batch i-2 is done with this table
+            if tr:
+                tr["prune0"].record(pstream)
             peaks, count, _ = node.native_peaks.find(m)                            # fill_powermap + find_valid_peak_new
             n_p, off_p, wid_p, pk_p = node.native_select.select(m, peaks, count)   # local_source_adaptive
             native.build_shift_table(n_p, off_p, self.cap, shifts_dev, mi_dev, ntot_dev)
@@ -318,6 +328,8 @@ class C2Pipeline:
             # the shift-stack (and the host's count read) wait for the table only, not for the result copies below
             pruned = torch.cuda.Event()
             pruned.record(pstream)
+            if tr:
+                tr["prune1"].record(pstream)
             if timing_stages:
                 self.stage_events[-1][2].record(pstream)
             self.map_free[slot] = pruned
@@ -344,6 +356,8 @@ class C2Pipeline:
             n_rows = min(int(self.ntot_pin[slot][0]), self.cap)
         sstream.wait_event(pruned)
         with torch.cuda.stream(sstream):
+            if tr:
+                tr["stack0"].record(sstream)
             if self.mode == "plain":
                 fe.stack_counted(src, shifts_dev, mi_dev, ntot_dev, n_rows, events=events)
             else:
@@ -352,6 +366,8 @@ class C2Pipeline:
                                       max_lag=self.max_lag, events=events)
             self.table_free[slot] = torch.cuda.Event()
             self.table_free[slot].record(sstream)
+            if tr:
+                tr["stack1"].record(sstream)
             if timing_stages:
                 self.stage_events[-1][3].record(sstream)
         if events is not None:
@@ -589,6 +605,49 @@ def run_b200(args, rank, world):
                               "per-mixture correlation tables are rebuilt for every sub-batch (24 us per mixture for ~35 "
                               "coarse patches each: amortised over ~600 patches in the fine stage, see c3)"}
 
+    # ---- where the pipelined step's time goes: one traced step (events around every stage on its own stream), then
+    # interval arithmetic on the host.  A stage's interval starts when its stream reaches it, so waits for SMs held by
+    # another stage's kernels show up as stretched intervals, not as gaps.
+    overlap = None
+    if args.streams == 3:
+        timed(1)
+        pipe.trace = []
+        base = torch.cuda.Event(enable_timing=True)
+        barrier()
+        base.record()
+        run_step()
+        pipe.join()
+        torch.cuda.synchronize()
+        tr, pipe.trace = pipe.trace, None
+
+        def iv(a, b):
+            return [(base.elapsed_time(t[a]), base.elapsed_time(t[b])) for t in tr]
+
+        def union(ivs):
+            tot, end = 0.0, -1.0
+            for lo, hi in sorted(ivs):
+                if hi > end:
+                    tot += hi - max(lo, end)
+                    end = hi
+            return tot
+
+        def inter(xs, ys):
+            return union(xs) + union(ys) - union(xs + ys)
+        sc, prn, stk = iv("score0", "score1"), iv("prune0", "prune1"), iv("stack0", "stack1")
+        wall = max(hi for _, hi in stk) - min(lo for lo, _ in sc)
+        n = len(tr)
+        overlap = {"sub_batches_traced": n, "wall_ms_per_sub_batch": wall / n,
+                   "score_busy_ms_per_sub_batch": union(sc) / n, "prune_busy_ms_per_sub_batch": union(prn) / n,
+                   "stack_busy_ms_per_sub_batch": union(stk) / n,
+                   "score_and_stack_concurrent_ms_per_sub_batch": inter(sc, stk) / n,
+                   "prune_and_stack_concurrent_ms_per_sub_batch": inter(prn, stk) / n,
+                   "nothing_running_ms_per_sub_batch": (wall - union(sc + prn + stk)) / n,
+                   "serial_sum_ms_per_sub_batch": kp_plain["score_ms"] + kp_plain["prune_ms"] + kp_plain["stack_ms"],
+                   "note": "intervals measured with CUDA events on the three streams during one pipelined step; a stage's "
+                           "interval includes the time its kernels wait for SMs (the scoring kernels and the shift-stack do "
+                           "not co-reside: each owns the register file while it runs), so `concurrent` is time the two "
+                           "stages were both in flight, and wall - serial_sum is what the pipelining really saves"}
+
     # ---- self-check (untimed): the 3-stream pipeline must produce exactly what the serial schedule produces -- maps,
     # top-K, peak counts, patch counts, the device-built shift tables and the stacked ring buffers
     def snapshot(serial):
@@ -704,6 +763,8 @@ def run_b200(args, rank, world):
         "selfcheck": "pipelined sub-batch == serial sub-batch (maps, top-K, peak / patch counts, shift tables, stacked ring checksums)",
         "clocks": clocks,
     }
+    if overlap:
+        line["stages"]["pipelined"] = overlap
     if fused_step:
         line["fused_norm_step"] = fused_step
     if ablation:

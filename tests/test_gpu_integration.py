@@ -603,6 +603,60 @@ def test_device_subdivision_beyond_nine_mics_equals_oracle(cuda_device, n_mics, 
     assert n_leaves > 20
 
 
+def test_device_fine_table_equals_oracle_patch_list(cuda_device, desk):
+    """pipeline.FrontEnd.fine_table (asw_subdivide on a padded batch of candidates + asw_build_fine_table) against the
+    oracle's restatement of Spotform_Small_Patch_Parallel's patch-list assembly (sep/Mic_Array.py:244-262) for every
+    coarse patch of two full-size mixtures: row order, offsets, owning mixture, per-candidate row ranges; then the
+    counted fused shift-stack + normalize of those rows (correlation tables) against the oracle on sampled rows."""
+    import copy
+    from oracle import subdivide_oracle
+    from acousticswarms_speech_b200.pipeline import FrontEnd
+    g, scene, mix, ma = desk
+    fe = FrontEnd(ma.SRP_node)
+    geo = oracle_geometry(scene)
+    mixes = np.stack([mix, synth.mixture(scene, 4, mix.shape[1], seed=71)])
+    x = torch.from_numpy(mixes).cuda()
+    smap = fe.score(x)[0]
+    n_sel, off, wid, pk = fe.select(smap)
+    P = off.shape[1]
+    cap = 2 * 64 * 64
+    shifts, mi, ci, cstart, ntot, status, cnt = fe.fine_table(n_sel, off, wid, cap)
+    assert int(status.max()) == 0 and int(cnt.max()) <= 128
+    total = int(ntot[0])
+    sh, mih, cih, cs = shifts[:total].cpu().numpy(), mi[:total].cpu().numpy(), ci[:total].cpu().numpy(), cstart.cpu().numpy()
+    maps = smap.cpu().numpy()
+    want_off, want_mi, want_rows = [], [], []
+    for b in range(2):
+        ocands = copy.deepcopy(opatches_of(geo, maps[b], scene))
+        assert len(ocands) == int(n_sel[b])
+        ototal, oindex = subdivide_oracle.small_patch_list(ocands, scene.mic_positions)
+        want_off += [p.sample_offset for p in ototal]
+        want_mi += [b] * len(ototal)
+        want_rows += [(b * P + q, oindex[q + 1] - oindex[q]) for q in range(len(ocands))]
+    assert total == len(want_off) > 1000
+    assert (sh[:, 0] == 0).all() and np.array_equal(sh[:, 1:], np.array(want_off)) and np.array_equal(mih, np.array(want_mi))
+    for slot, nrows in want_rows:
+        assert cs[slot + 1] - cs[slot] == nrows and (cih[cs[slot]:cs[slot + 1]] == slot).all()
+    assert cs[-1] == total
+    # the rows feed the counted, table-driven fused normalize: sampled rows against the oracle
+    L = native.CorrTables.lag_for_geometry(scene.mic_positions, 48000)
+    tabs = native.CorrTables(mixes.shape[1], cuda_device, max_lag=L).compute(x)
+    seen = []
+    fe.net_batch = 64
+    fe.stack_norm_counted(x, shifts, mi, ntot, total, tables=tabs, max_lag=L,
+                          consumer=lambda out, mu, sd, first, n: seen.append((first, out[:n:37].cpu().numpy(), sd[:n:37].cpu().numpy())))
+    checked = 0
+    for first, out, sd in seen[::5]:
+        for j in range(out.shape[0]):
+            r = first + 37 * j
+            stacked = shift_oracle.roll_by_gather(mixes[mih[r]], -sh[r].astype(np.int64))[None]
+            dn, mu, wsd = shift_oracle.normalize_input(stacked)
+            assert abs(sd[j, 0, 0] - wsd[0, 0, 0]) <= 1e-5 * wsd[0, 0, 0]
+            assert np.abs(out[j] - dn[0]).max() <= TOL * np.abs(dn[0]).max()
+            checked += 1
+    assert checked >= 8
+
+
 class HalfMeanNet(torch.nn.Module):
     """The network whose DataParallelSpotModel reproduces oracle/make_golden.py's DelayAndSumSpot on 16-bit PCM content:
     (normalised mean over mics) x {1 coarse, 0.5 fine}; unnormalize restores the scale, the callers remove the mean."""
