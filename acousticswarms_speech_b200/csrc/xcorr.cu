@@ -435,15 +435,6 @@ int asw_corr_tables(asw_corr_t* h, const float* mix_dev, int B, int T, double* t
     // launches with tails against 3, while the extra HBM traffic is ~5 us per mixture.
     const size_t spec_per = (size_t)p.nblk * p.U2 * kNc;          // float2 per mixture
     int chunk = (int)(kSpecBudget / (spec_per * sizeof(float2)));
-    if (chunk < 1) chunk = 1;
-    if (chunk > B) chunk = B;
-    int rc;
-    if ((rc = grow(&h->d_spec, &h->spec_cap, spec_per * chunk)) != ASW_OK) return rc;
-    if ((rc = grow(&h->d_part, &h->part_cap, (size_t)chunk * p.ngrp * p.P * kNc)) != ASW_OK) return rc;
-    if ((rc = grow(&h->d_sums, &h->sums_cap, (size_t)chunk * p.nblk * h->M * 2)) != ASW_OK) return rc;
-    p.spec = h->d_spec;
-    p.part = h->d_part;
-    p.sums = h->d_sums;
     Tiles tiles{};
     for (int i0 = 0; i0 < h->M - 1; i0 += kTI)
         for (int j0 = i0; j0 < h->M; j0 += kTJ) {
@@ -451,6 +442,17 @@ int asw_corr_tables(asw_corr_t* h, const float* mix_dev, int B, int T, double* t
             tiles.j0[tiles.n] = (unsigned char)j0;
             ++tiles.n;
         }
+    if (chunk < 1) chunk = 1;
+    if (chunk > B) chunk = B;
+    if (chunk > 65535 / tiles.n) chunk = 65535 / tiles.n;        // gridDim.z of the pair kernel, gridDim.y of the inverse
+    int rc;
+    if ((rc = grow(&h->d_spec, &h->spec_cap, spec_per * chunk)) != ASW_OK) return rc;
+    if ((rc = grow(&h->d_part, &h->part_cap, (size_t)chunk * p.ngrp * p.P * kNc)) != ASW_OK) return rc;
+    if ((rc = grow(&h->d_sums, &h->sums_cap, (size_t)chunk * p.nblk * h->M * 2)) != ASW_OK) return rc;
+    p.spec = h->d_spec;
+    p.part = h->d_part;
+    p.sums = h->d_sums;
+
     static PerDeviceOnce attr_once;
     const size_t smem_fft = (size_t)kXWarps * kTile * sizeof(float);
     if (attr_once.need()) {

@@ -227,3 +227,58 @@ def test_shift_stack_skips_rows_with_foreign_mixture_index(cuda_device):
     out = torch.full((3, M, T), 123.0, device=cuda_device)
     native.shift_stack(x, sh, mi, out=out)
     assert torch.equal(out[0], x[0]) and bool((out[1:] == 123.0).all())
+
+
+def test_corr_tables_argument_errors_and_empty_batches(cuda_device):
+    """Error behaviour of the table entry points: short signals are refused (callers take the exact pass), mismatched
+    tables are refused, empty patch lists return empty results."""
+    from acousticswarms_speech_b200 import _lib, native
+    ct = native.CorrTables(3, cuda_device, max_lag=64)
+    with pytest.raises(_lib.AswError):
+        ct.compute(torch.zeros((1, 3, 4095), device=cuda_device))          # T < 4096
+    with pytest.raises(_lib.AswError):
+        ct.compute(torch.zeros((1, 4, 8192), device=cuda_device))          # wrong channel count
+    with pytest.raises(_lib.AswError):
+        native.CorrTables(3, cuda_device, max_lag=513)
+    x = torch.randn((2, 3, 8192), device=cuda_device)
+    tab = ct.compute(x)
+    sh = torch.zeros((0, 3), dtype=torch.int32, device=cuda_device)
+    out, mu, sd = native.shift_stack_norm(x, sh, torch.zeros((0,), dtype=torch.int32, device=cuda_device), tables=tab, max_lag=64)
+    assert out.shape == (0, 3, 8192) and mu.shape == (0, 1, 1)
+    sh = torch.zeros((2, 3), dtype=torch.int32, device=cuda_device)
+    with pytest.raises(_lib.AswError):                                       # table of another max_lag
+        native.shift_stack_norm(x, sh, tables=tab, max_lag=32)
+    with pytest.raises(_lib.AswError):                                       # tables of another batch
+        native.shift_stack_norm(x, sh, tables=tab[:1].contiguous(), max_lag=64)
+    # all-zero channels: variance 0 -> the exact pass decides (std 0, like torch's), no NaN from the table path
+    z = torch.zeros((1, 3, 8192), device=cuda_device)
+    a = native.shift_stack_norm(z, sh[:1].contiguous(), tables=ct.compute(z), max_lag=64)
+    b = native.shift_stack_norm(z, sh[:1].contiguous())
+    assert torch.equal(a[2], b[2]) and float(a[2].max()) == 0.0
+
+
+def test_fine_table_with_empty_candidate_slots(cuda_device):
+    """asw_build_fine_table on a padded candidate list: slots with width <= 0 contribute nothing, the others their
+    leaves followed by their own (checked-out) offsets; the capacity clamps the total."""
+    from acousticswarms_speech_b200 import native
+    n, L, D = 5, 4, 3
+    cnt = torch.tensor([2, 0, 9, 1, 3], dtype=torch.int32, device=cuda_device)       # 9 > L: clamped to L leaves
+    off = torch.arange(n * L * D, dtype=torch.int32, device=cuda_device).reshape(n, L, D)
+    root = -torch.arange(n * 2 * D, dtype=torch.int32, device=cuda_device).reshape(n, 2, D)
+    wid = torch.tensor([8, 0, 8, -1, 4], dtype=torch.int32, device=cuda_device)
+    own = torch.tensor([0, 0, 1, 1, 2], dtype=torch.int32, device=cuda_device)
+    sh, mi, ci, cs, nt = native.build_fine_table(cnt, off, root, wid, own, 64)
+    want_rows, want_mi, want_ci = [], [], []
+    for i in (0, 2, 4):
+        k = min(int(cnt[i]), L)
+        want_rows += [[0] + off[i, q].tolist() for q in range(k)] + [[0] + root[i, 0].tolist()]
+        want_mi += [int(own[i])] * (k + 1)
+        want_ci += [i] * (k + 1)
+    total = int(nt[0])
+    assert total == len(want_rows) == 3 + 5 + 4
+    assert sh[:total].tolist() == want_rows and mi[:total].tolist() == want_mi and ci[:total].tolist() == want_ci
+    assert cs.tolist() == [0, 3, 3, 8, 8, 12]
+    sh2, mi2, ci2, cs2, nt2 = native.build_fine_table(cnt, off, root, wid, own, 7)
+    assert int(nt2[0]) == 7 and sh2[:7].tolist() == want_rows[:7]
+    nothing = native.build_fine_table(cnt, off, root, torch.zeros_like(wid), own, 8)
+    assert int(nothing[4][0]) == 0

@@ -212,3 +212,19 @@ def test_fine_stage_tdoa_rows_follow_the_array_rate():
         pc = find_merge_center(np.round(off1[pick[0]]), area, scene.mic_positions, np.zeros(3), fs)
         inside = np.all(np.abs(off1[pick] - np.round(off1[pick[0]])) <= 1.5 + 1e-3, axis=1)
         assert pc.area_points is not None and pc.area_points.shape[1] == int(inside.sum()) >= 1
+
+
+def test_corr_table_lag_range_from_geometry():
+    """CorrTables.lag_for_geometry: the largest pair TDoA of the array plus the hypercube width, in 32-sample steps,
+    capped at the kernel's 512; every coarse patch of a geometry must fit (|r_c' - r_c| <= lag for all pairs)."""
+    scene = synth.desk_array(7, np.random.default_rng(1), 48000)
+    L = native.CorrTables.lag_for_geometry(scene.mic_positions, 48000)
+    d = np.sqrt(((scene.mic_positions[:, None] - scene.mic_positions[None]) ** 2).sum(-1)).max()
+    assert L % 32 == 0 and 32 <= L <= 512 and L >= d / 343.0 * 48000 + 8
+    assert native.CorrTables.lag_for_geometry(scene.mic_positions, 44100) <= L
+    far = np.array([[0.0, 0.0, 0.0], [9.0, 0.0, 0.0]])
+    assert native.CorrTables.lag_for_geometry(far, 48000) == 512            # beyond the table: those patches take the exact pass
+    node = host_node(scene.mic_positions, scene.roi)
+    offs = np.array([c.sample_offset for c in node.clusters])              # every hypercube centre the geometry can produce
+    r = np.concatenate([np.zeros((offs.shape[0], 1)), offs], axis=1)
+    assert np.abs(r[:, :, None] - r[:, None, :]).max() + 8 <= L
