@@ -192,7 +192,7 @@ struct Tiles {
 };
 
 // K2: conj(A_i) B_j summed over the blocks of one group; thread = bin, the tile's 32 accumulators in registers.
-__global__ void __launch_bounds__(kPairThreads) xcorr_pair_kernel(XP p, Tiles tiles) {
+__global__ void __launch_bounds__(kPairThreads, 2) xcorr_pair_kernel(XP p, Tiles tiles) {   // <= 128 registers: 2 CTAs per SM
     const int k = blockIdx.x * kPairThreads + threadIdx.x;      // bin 0..1023
     const int grp = blockIdx.y;
     const int t = blockIdx.z % tiles.n, b = blockIdx.z / tiles.n;
