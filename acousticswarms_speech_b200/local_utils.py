@@ -25,6 +25,42 @@ def si_sdr(estimated_signal, reference_signals, scaling=True):
     return 10 * math.log10((e_true ** 2).sum() / ((e_res ** 2).sum() + MIN_ERR))
 
 
+def split_wav(wav, top_db=18):
+    """Non-silent segments of an output, 1000 .. 4000+ samples each (eval_utils.py:43-70).  Like the reference this
+    needs ``librosa`` (``feature.rms`` and ``effects.split``); it is imported here, on first use, because nothing else
+    on the path does."""
+    import librosa
+    MIN_SEG, MAX_SEG = 1000, 4000
+    power_list = librosa.feature.rms(y=wav, frame_length=1024, hop_length=256)
+    max_ref = np.amax(power_list)
+    split_threshold = 0.04
+    if max_ref < split_threshold:
+        intervals = librosa.effects.split(wav, top_db=top_db, ref=split_threshold, frame_length=1024, hop_length=256)
+    else:
+        intervals = librosa.effects.split(wav, top_db=top_db, frame_length=1024, hop_length=256)
+    finetune_seg = []
+    for indexes in intervals:
+        interval_len = indexes[1] - indexes[0]
+        if interval_len < MIN_SEG:
+            continue
+        elif interval_len > MAX_SEG:
+            num_seg = interval_len // MAX_SEG
+            for i in range(num_seg):
+                if i >= num_seg - 1:
+                    finetune_seg.append([indexes[0] + i * MAX_SEG, indexes[1]])
+                else:
+                    finetune_seg.append([indexes[0] + i * MAX_SEG, indexes[0] + (i + 1) * MAX_SEG])
+        else:
+            finetune_seg.append([indexes[0], indexes[1]])
+    return finetune_seg
+
+
+def split_wise_sisdr(estimated_signal, reference_signals, seg_index):
+    """SI-SDR of every segment (eval_utils.py:73-82)."""
+    assert len(seg_index) > 0
+    return [si_sdr(estimated_signal[a:b], reference_signals[a:b]) for a, b in seg_index]
+
+
 def max_avg_power(x, window_size=12000):
     """Largest RMS over any ``window_size`` box and the samples of that box (:13-17)."""
     e = uniform_filter1d(x ** 2, size=window_size, mode="constant", origin=-window_size // 2)

@@ -11,10 +11,22 @@ import torch
 
 from .constants import (FS, INIT_WIDTH, SPEED_OF_SOUND, SPOT_POWER_THRESHOLD2, SRP_THRESHOLDS,
                         USE_RELATIVE_SPOT_POWER, freq_bins, n_fft, window_length)
-from .local_utils import _tdoa_rows, binary_search_baseline, max_avg_power, search_area, si_sdr
+from .local_utils import (_tdoa_rows, binary_search_baseline, max_avg_power, search_area, si_sdr, split_wav,
+                          split_wise_sisdr)
 from .spot import si_sdr_from_gram
 from .patch import Patch
 from .srp_phat import SRP_PHAT
+
+
+def check_sisnr_win(sisnr_list, SISNR_THRESHOLD=-2, SISNR_THRESHOLD2=-7):
+    """Window-wise SI-SDR check (Mic_Array.py:18-28): some window above the first threshold, none below the second."""
+    same, none_below = False, True
+    for value in sisnr_list:
+        if value > SISNR_THRESHOLD:
+            same = True
+        if value < SISNR_THRESHOLD2:
+            none_below = False
+    return same and none_below
 
 
 def weight_mean_pos(patch_list, powers, id_lists):
@@ -261,3 +273,58 @@ class Mic_Array(object):
                 output_pair.append((patch_center, audio, powers[cluster_id],
                                     str(i) + "_" + str(cluster_id), save_offsets, big_label))
         return output_pair
+
+    def Clustering_new(self, output_pair, simple_pos=None, sample_gt=None):
+        """Non-maximum suppression over the fine-stage outputs (Mic_Array.py:399-500): candidates by descending power;
+        one joins an existing cluster when its SI-SDR against the cluster head exceeds -1 dB, or the window-wise SI-SDRs
+        pass ``check_sisnr_win``, or the heads are closer than 0.45 m in the plane; the maximum over all heads of the
+        window-wise SI-SDRs can also veto a new cluster.  -> (audio_final, patch_final, spot_times, wrong_spotforming).
+        Host code on a handful of rows, downstream of the accelerated path; kept so that
+        ``JointModel.localize_by_separation`` (sep/training/JointModel/network.py:151-199) runs on the drop-in class."""
+        SI_SDR_THRESHOLD = -1
+        candidates = sorted(output_pair, key=lambda x: -x[2])
+        clusters = {}
+        wrong_spotforming = []
+        for _id in range(len(candidates)):
+            belong_cluster = -1
+            unique = True
+            sisnr_seg = []
+            big_label = candidates[_id][-1]
+            center1 = candidates[_id][0].center_pos()
+            audio1 = candidates[_id][1]
+            power1 = candidates[_id][2]
+            seg_win = split_wav(audio1)
+            if len(seg_win) == 0:
+                continue
+            for cluster_id in clusters:
+                final_candidate_id = clusters[cluster_id][0]
+                audio2 = candidates[final_candidate_id][1]
+                center2 = candidates[final_candidate_id][0].center_pos()
+                similarity = si_sdr(audio1, audio2)
+                sisdr_list = split_wise_sisdr(audio1, audio2, seg_win)
+                sisnr_seg.append(sisdr_list)
+                dis = np.linalg.norm(center1[:2] - center2[:2])
+                if (similarity > SI_SDR_THRESHOLD) or check_sisnr_win(sisdr_list) or dis < 0.45:
+                    clusters[final_candidate_id].append(_id)
+                    unique = False
+                    belong_cluster = cluster_id
+                    break
+            if len(sisnr_seg) != 0:
+                if check_sisnr_win(np.amax(np.array(sisnr_seg), axis=0), SISNR_THRESHOLD=-1, SISNR_THRESHOLD2=-5):
+                    unique = False
+            if unique:
+                clusters[_id] = [_id]
+            elif big_label >= 0 and sample_gt is not None and belong_cluster >= 0:
+                final_candidate_id = clusters[belong_cluster][0]
+                cluster_label = candidates[final_candidate_id][-1]
+                power2 = candidates[final_candidate_id][2]
+                offset1 = candidates[final_candidate_id][-2]["audio_offset"]
+                delta_offset = (offset1 - sample_gt[:, big_label]).astype(int)
+                if cluster_label == -1:
+                    wrong_spotforming.append((big_label, cluster_label, delta_offset, power1 / power2))
+        patch_final, audio_final = [], []
+        for cluster_id in clusters:
+            final_candidate_id = clusters[cluster_id][0]
+            patch_final.append(candidates[final_candidate_id])
+            audio_final.append(candidates[final_candidate_id][1])
+        return audio_final, patch_final, self.big_spotforming_times + self.spotforming_times, wrong_spotforming

@@ -28,6 +28,13 @@ Contents
 ``subdivide_oracle`` search_area / binary_area_divide_width /
                   binary_search_baseline (sep/helpers/local_utils_3d.py:13-17,
                   212-388).
+``spotform_oracle`` everything Spotform_Small_Patch_Parallel does after the network
+                  (sep/Mic_Array.py:32-81, 267-383) and Clustering_new (:18-28, 399-500,
+                  sep/helpers/eval_utils.py:43-82).
+``fake_librosa``  deterministic stand-in for the two librosa calls of split_wav
+                  (librosa is absent here); used for BOTH the reference run that
+                  makes the fixtures and the tests -- it pins everything of
+                  Clustering_new except librosa itself (**unpinned**, like A1).
 ``ref_loader``    imports the UNMODIFIED reference from /root/reference under
                   inert stubs for its absent third-party packages (only works in
                   the build container; used to pin the restatements and to

@@ -138,7 +138,14 @@ def spotform_fixture(ns, name, scene, n_spk, T, seed, max_candidates):
     pairs = MA.Spotform_Small_Patch_Parallel(torch.tensor(mix), cands, spot)
     D = scene.mic_positions.shape[0] - 1
     centres = [pc.center_pos() for pc, *_ in pairs]
+    # Clustering_new (sep/Mic_Array.py:399-500) on those outputs.  Its split_wav calls librosa, which is absent here: the
+    # reference runs with oracle/fake_librosa.py installed as eval_utils' librosa (everything else is the reference's).
+    from oracle import fake_librosa
+    sys.modules["sep.helpers.eval_utils"].librosa = fake_librosa
+    audio_final, patch_final, spot_times, _ = MA.Clustering_new([(pc, a.copy(), p, t, o, l) for pc, a, p, t, o, l in pairs])
     out = {
+        "final_tags": np.array([p[3] for p in patch_final]), "final_spot_times": spot_times,
+        "final_audio_sha": np.array([sha(np.asarray(a, dtype=np.float32)) for a in audio_final]),
         "mic_positions": scene.mic_positions, "roi": np.array(scene.roi), "fs": scene.fs, "n_spk": n_spk, "T": T,
         "seed": seed, "mix_sha": sha(mix), "max_candidates": max_candidates,
         "patch_offsets": np.array([p.sample_offset for p in patches], dtype=np.int64).reshape(len(patches), D),
@@ -161,7 +168,7 @@ def spotform_fixture(ns, name, scene, n_spk, T, seed, max_candidates):
     }
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
     print(f"{name}: patches={len(patches)} kept={len(kept)} candidates={len(cands)} fine={MA.spotforming_times} "
-          f"outputs={len(pairs)} tags={list(out['tags'])}")
+          f"outputs={len(pairs)} tags={list(out['tags'])} final={list(out['final_tags'])}")
 
 
 def main():

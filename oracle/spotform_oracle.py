@@ -132,3 +132,60 @@ def small_patch_parallel(mix, candidates, spot_model, mic, min_trigger_power=0.5
             out.append((pc, sep[cluster_id, :], powers[cluster_id], str(i) + "_" + str(cluster_id),
                         {"audio_offset": patches[cluster_id].sample_offset, "localization_offset": offsets}, -1))
     return out
+
+
+# ---- Clustering_new (sep/Mic_Array.py:399-500) with split_wav / split_wise_sisdr (sep/helpers/eval_utils.py:43-82) -------
+def check_sisnr_win(values, t1=-2, t2=-7):
+    """sep/Mic_Array.py:18-28."""
+    return any(v > t1 for v in values) and not any(v < t2 for v in values)
+
+
+def split_wav(wav, librosa, top_db=18):
+    """eval_utils.py:43-70 around the two librosa calls (``librosa``: the module to use -- the real one, or
+    oracle/fake_librosa.py in tests)."""
+    power = librosa.feature.rms(y=wav, frame_length=1024, hop_length=256)
+    if np.amax(power) < 0.04:
+        intervals = librosa.effects.split(wav, top_db=top_db, ref=0.04, frame_length=1024, hop_length=256)
+    else:
+        intervals = librosa.effects.split(wav, top_db=top_db, frame_length=1024, hop_length=256)
+    segs = []
+    for a, b in intervals:
+        n = b - a
+        if n < 1000:
+            continue
+        if n > 4000:
+            k = n // 4000
+            for i in range(k):
+                segs.append([a + i * 4000, b if i >= k - 1 else a + (i + 1) * 4000])
+        else:
+            segs.append([a, b])
+    return segs
+
+
+def clustering_new(output_pair, librosa, spot_times=0):
+    """sep/Mic_Array.py:399-500 without ground truth -> (audio_final, patch_final, spot_times, [])."""
+    cands = sorted(output_pair, key=lambda x: -x[2])
+    clusters = {}
+    for i in range(len(cands)):
+        unique = True
+        centre1, audio1 = cands[i][0].center_pos(), cands[i][1]
+        segs = split_wav(audio1, librosa)
+        if len(segs) == 0:
+            continue
+        per_head = []
+        for cid in clusters:
+            head = clusters[cid][0]
+            audio2, centre2 = cands[head][1], cands[head][0].center_pos()
+            sim = si_sdr(audio1, audio2)
+            win = [si_sdr(audio1[a:b], audio2[a:b]) for a, b in segs]
+            per_head.append(win)
+            if sim > -1 or check_sisnr_win(win) or np.linalg.norm(centre1[:2] - centre2[:2]) < 0.45:
+                clusters[head].append(i)
+                unique = False
+                break
+        if per_head and check_sisnr_win(np.amax(np.array(per_head), axis=0), -1, -5):
+            unique = False
+        if unique:
+            clusters[i] = [i]
+    heads = [clusters[c][0] for c in clusters]
+    return [cands[h][1] for h in heads], [cands[h] for h in heads], spot_times, []

@@ -699,6 +699,42 @@ def test_spotform_small_patch_parallel_output_matches_reference_golden(cuda_devi
     # float32 device arithmetic vs the reference's float32 numpy: powers / audio to 1e-5 relative; the localisation
     # offsets are power-weighted means of integer offsets a few samples apart, so 1e-5 on the weights is <= 2e-4 samples
     check_spotform_pairs(pairs, g, power_rtol=1e-5, offset_atol=2e-4, centre_atol=1e-9)
+    # ... and Clustering_new (sep/Mic_Array.py:399-500), the last call of localize_by_separation, on the device path's
+    # outputs: same cluster heads, in the same order, as the reference picked (both with oracle/fake_librosa.py standing
+    # in for the absent librosa, see that file)
+    import sys
+    from oracle import fake_librosa
+    saved = sys.modules.get("librosa")
+    sys.modules["librosa"] = fake_librosa
+    try:
+        audio_final, patch_final, spot_times, wrong = ma.Clustering_new(pairs)
+    finally:
+        if saved is None:
+            del sys.modules["librosa"]
+        else:
+            sys.modules["librosa"] = saved
+    assert [p[3] for p in patch_final] == [str(t) for t in g["final_tags"]] and wrong == []
+    assert spot_times == int(g["final_spot_times"]) and len(audio_final) == len(patch_final)
+    # the same chain through the caller's own entry point (JointModel.setup + localize_by_separation,
+    # sep/training/JointModel/network.py:125-199); with every kept candidate refined, not only the fixture's first few
+    if name == "small_spotform":
+        from acousticswarms_speech_b200.joint import JointLocalizer
+        jl = JointLocalizer(HalfMeanNet(), spot_batch_size=128)
+        jl.setup(scene.mic_positions, scene.roi)
+        proc = jl.Mic_processor
+        jl.setup(scene.mic_positions, scene.roi)
+        assert jl.Mic_processor is proc                                   # same geometry: the array is reused (:131-133)
+        sys.modules["librosa"] = fake_librosa
+        try:
+            patch_f, audio_f, srp_drop, stage1_drop, times = jl.localize_by_separation(x)
+        finally:
+            if saved is None:
+                del sys.modules["librosa"]
+            else:
+                sys.modules["librosa"] = saved
+        assert [p[3] for p in patch_f] == [str(t) for t in g["final_tags"]]     # the small scene keeps <= max_candidates
+        assert audio_f.shape == (len(patch_f), mix.shape[1]) and (srp_drop, stage1_drop) == (0, 0)
+        assert times == int(g["final_spot_times"])
 
 
 @pytest.mark.parametrize("n_spk,seed,noise", [(5, 101, 1e-3), (8, 102, 1e-2), (0, 103, 1e-3)])
