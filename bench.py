@@ -602,8 +602,8 @@ def run_b200(args, rank, world):
                       "value": world * NSUB * B * G / (ms_norm / args.steps / 1e3), "unit": UNIT,
                       "stack_stage_ms_per_sub_batch": kp_norm["stack_ms"], "prune_stage_ms_per_sub_batch": kp_norm["prune_ms"],
                       "note": "same step, shift-stack fused with normalize_input (what shift_and_sep feeds the network); the "
-                              "per-mixture correlation tables are rebuilt for every sub-batch (24 us per mixture for ~35 "
-                              "coarse patches each: amortised over ~600 patches in the fine stage, see c3)"}
+                              "per-mixture correlation tables are rebuilt for every sub-batch (~15 us per mixture for its ~35 "
+                              "coarse patches; in the fine stage the same tables serve ~800 patches, see c3)"}
 
     # ---- where the pipelined step's time goes: one traced step (events around every stage on its own stream), then
     # interval arithmetic on the host.  A stage's interval starts when its stream reaches it, so waits for SMs held by

@@ -129,7 +129,7 @@ def _circ_corr(a, b, lag):
     return float(np.dot(a, np.roll(b, -lag)))
 
 
-@pytest.mark.parametrize("M,T,L", [(3, 8192, 512), (7, 144000, 512), (4, 132300, 300), (2, 4099, 100)])
+@pytest.mark.parametrize("M,T,L", [(3, 8192, 512), (7, 144000, 512), (4, 132300, 300), (2, 4099, 100), (16, 20000, 128), (32, 8200, 40)])
 def test_corr_tables_match_direct_correlation(cuda_device, M, T, L):
     """S_c, E_c exact; R_cc'(l) within fp32-FFT round-off of the float64 circular correlation of the re-quantised
     channels, for every pair at the table's edges and at random lags (T odd exercises the scalar loader, the last
@@ -152,7 +152,7 @@ def test_corr_tables_match_direct_correlation(cuda_device, M, T, L):
             for j in range(i + 1, M):
                 row = tab[b, 2 * M + p * (2 * L + 1): 2 * M + (p + 1) * (2 * L + 1)]
                 scale = np.sqrt((q[b, i] ** 2).sum() * (q[b, j] ** 2).sum())
-                for lag in [-L, -L + 1, -1, 0, 1, L - 1, L] + list(rng.integers(-L, L + 1, size=6)):
+                for lag in [-L, -L + 1, -1, 0, 1, L - 1, L] + list(rng.integers(-L, L + 1, size=6 if M <= 8 else 1)):
                     worst = max(worst, abs(row[lag + L] - _circ_corr(q[b, i], q[b, j], int(lag))) / scale)
                 p += 1
     print(f"corr tables M={M} T={T} L={L}: worst |dR| / sqrt(E_i E_j) = {worst:.2e}")
