@@ -14,6 +14,11 @@
 
 namespace asw {
 
+int carve_all() {
+    static const int v = [] { const char* e = getenv("ASW_CARVE"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
@@ -262,7 +267,7 @@ int asw_srp_create(asw_srp_t** out, int device, int M, int G, const double* lag,
     }
     DeviceGuard guard(device);      // the caller's current device is restored on return
     if (!guard.ok) {
-        set_error("cannot make device %d current", device);
+        set_error("cannot make CUDA device %d current (no CUDA device, or a bad index)", device);
         return ASW_ERR_CUDA;
     }
 

@@ -67,6 +67,18 @@ struct PerDeviceOnce {
     }
 };
 
+// One shared-memory carve-out for every kernel of the pipelined path (ASW_CARVE=<percent of the maximum>): an SM changes its L1 / shared
+// split only when it is empty, so CTAs of kernels that prefer different splits never share an SM and streams that
+// should overlap take turns instead.
+int carve_all();
+#define ASW_CARVE_ONCE(kernel)                                                                              \
+    do {                                                                                                    \
+        static asw::PerDeviceOnce _carve_once;                                                              \
+        if (asw::carve_all() && _carve_once.need())                                                         \
+            ASW_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,     \
+                                                asw::carve_all()));                                         \
+    } while (0)
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }

@@ -231,6 +231,7 @@ int launch_gcc(const GccParams& p, cudaStream_t s) {
         if (attr_once.need()) {
             ASW_CUDA_CHECK(cudaFuncSetAttribute(gcc_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
+        ASW_CARVE_ONCE(gcc_fft_kernel);
         gcc_fft_kernel<<<grid, 32 * kFftWarps, smem, s>>>(p);
         ASW_LAUNCH_CHECK("gcc_fft_kernel");
         return ASW_OK;

@@ -165,7 +165,7 @@ int asw_peaks_create(asw_peaks_t** out, int device, int Lx, int Ly, int Lz, int 
     *out = nullptr;
     DeviceGuard guard(device);      // the caller's current device is restored on return
     if (!guard.ok) {
-        set_error("cannot make device %d current", device);
+        set_error("cannot make CUDA device %d current (no CUDA device, or a bad index)", device);
         return ASW_ERR_CUDA;
     }
     asw_peaks* h = new asw_peaks();
@@ -231,6 +231,9 @@ int asw_peaks_find(asw_peaks_t* h, const float* map_dev, int B, int32_t* peaks_d
         ASW_CUDA_CHECK(cudaMalloc(&h->d_first, (size_t)B * h->G * sizeof(int)));
         h->Bcap = B;
     }
+    ASW_CARVE_ONCE(map_max_kernel);
+    ASW_CARVE_ONCE(peak_flag_kernel);
+    ASW_CARVE_ONCE(peak_collect_kernel);
     map_max_kernel<<<B, 1024, 0, s>>>(map_dev, h->G, max_power_dev, h->d_first);
     ASW_LAUNCH_CHECK("map_max_kernel");
     PeakParams p{};

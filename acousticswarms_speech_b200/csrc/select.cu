@@ -1223,7 +1223,7 @@ int asw_select_create(asw_select_t** out, int device, int G, int D, int W, const
     }
     DeviceGuard guard(device);      // the caller's current device is restored on return
     if (!guard.ok) {
-        set_error("cannot make device %d current", device);
+        set_error("cannot make CUDA device %d current (no CUDA device, or a bad index)", device);
         return ASW_ERR_CUDA;
     }
     asw_select* h = new asw_select();
@@ -1357,6 +1357,7 @@ int asw_select_patches(asw_select_t* h, const float* map_dev, const int32_t* pea
     if (smem > 16 * 1024) {
         ASW_CUDA_CHECK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+    ASW_CARVE_ONCE(select_kernel);
     select_kernel<<<B, kSelThreads, smem, (cudaStream_t)stream>>>(p);
     ASW_LAUNCH_CHECK("select_kernel");
     return ASW_OK;
@@ -1468,6 +1469,7 @@ int asw_build_shift_table(const int32_t* count_dev, const int32_t* offsets_dev, 
         set_error("asw_build_shift_table: null argument or bad shape (B <= 1024)");
         return ASW_ERR_ARG;
     }
+    ASW_CARVE_ONCE(build_shift_table_kernel);
     build_shift_table_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(count_dev, offsets_dev, B, max_patches, D, shifts_dev,
                                                                   mix_index_dev, n_total_dev, capacity);
     ASW_LAUNCH_CHECK("build_shift_table_kernel");

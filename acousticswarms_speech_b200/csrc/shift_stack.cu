@@ -12,6 +12,10 @@
 // The fused variant also applies normalize_input (sep/training/SpeakerLocalization/network.py:28-40):
 // x = round(x * 2^15) / 2^15; ref = mean over mics; (x - mean_t(ref)) / std_t(ref) (unbiased).
 #include <limits.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
 
 #include "common.cuh"
 
@@ -119,6 +123,180 @@ __global__ void __launch_bounds__(kThreads) shift_stack_vec_kernel(const float* 
         case 1: shift_row_chunk<NORM, 1>(src, dst, r, T, mean, sd); break;
         case 2: shift_row_chunk<NORM, 2>(src, dst, r, T, mean, sd); break;
         default: shift_row_chunk<NORM, 3>(src, dst, r, T, mean, sd); break;
+    }
+}
+
+// Persistent variant (ASW_STACK=persist, opt-in; the default stays the kernel above): ONE resident CTA per SM, 16 warps
+// x 64 registers = half of the register file, a quarter of the thread slots, no shared memory.  It was written to let
+// scoring CTAs of another stream share the SMs with the HBM-bound copy; what the B200 measurements say
+// (profiles/r02_notes.md section 8, experiments/coresidency_probe.py):
+//  * alone it writes as fast as 6 x 256 threads per SM (0.779 vs 0.794 ms per 1152 patches): the bytes in flight, not
+//    the thread count, are what saturates HBM;
+//  * a grid larger than the machine never shares SMs with another grid (CTAs of the second grid are dispatched only
+//    once the first is fully dispatched), a persistent grid does, but only when every co-resident kernel asks for the
+//    SAME shared-memory carve-out (ASW_CARVE): an SM changes its L1 / shared split only when empty;
+//  * the loads in flight live in L1 lines, so the carve-out the STFT needs (164 KB) costs this kernel 7 % of its
+//    bandwidth, and the STFT next to a saturated HBM pipe runs at a third of its speed: the pair gains 0.13 ms of
+//    1.36 ms, the pipelined step nothing.  Hence opt-in.
+// A warp owns a contiguous run of 32 * VPT output vectors; lane l loads the ALIGNED source vectors
+// src4[(run + 32 v + l + r / 4) mod T/4] (one LDG.128 per output vector instead of two), and the r mod 4 samples it
+// misses come from its neighbour's registers by shuffle (lane 31 takes them from lane 0's next vector; one broadcast
+// load supplies the vector after the run).  4 * (VPT + 1) data registers hold 16 * VPT bytes in flight per thread.
+// Warps fetch work items (4 consecutive runs of one row) from an atomic counter, one item ahead of their use.
+__device__ __forceinline__ float4 ldg_nc_v4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+template <int O>
+__device__ __forceinline__ float4 funnel_next(float4 a, float4 nxt_for_lane0, int lane) {
+    if (O == 0) return a;
+    const int from = (lane + 1) & 31;
+    const bool l0 = lane == 0;
+    const float cx = __shfl_sync(0xffffffffu, l0 ? nxt_for_lane0.x : a.x, from);
+    if (O == 1) return make_float4(a.y, a.z, a.w, cx);
+    const float cy = __shfl_sync(0xffffffffu, l0 ? nxt_for_lane0.y : a.y, from);
+    if (O == 2) return make_float4(a.z, a.w, cx, cy);
+    const float cz = __shfl_sync(0xffffffffu, l0 ? nxt_for_lane0.z : a.z, from);
+    return make_float4(a.w, cx, cy, cz);
+}
+
+// A run that neither wraps around the end of the source row nor passes the end of the output row: every address is
+// one base plus an immediate.  p = src4 + s0 + lane, q = dst4 + run0 + lane.
+template <bool NORM, int O, int VPT>
+__device__ __forceinline__ void shift_run_fast(const float4* __restrict__ p, float4* __restrict__ q, int lane, float mean,
+                                               float sd) {
+    float4 a[VPT + 1];
+    // volatile asm keeps every load of the run ahead of the first store (ptxas otherwise interleaves them to save
+    // registers, and the bytes in flight per thread are the point of this kernel)
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) a[v] = ldg_nc_v4(p + 32 * v);
+    if (O != 0) a[VPT] = ldg_nc_v4(p + 32 * VPT - lane);      // the vector after the run (lane 31's neighbour): broadcast
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+        float4 x = funnel_next<O>(a[v], a[v + 1], lane);
+        if (NORM) x = norm4(x, mean, sd);
+        __stcs(q + 32 * v, x);
+    }
+}
+
+// The two runs per row that do wrap or end early (of ~100): one vector at a time, two aligned loads each.
+template <bool NORM>
+__device__ __noinline__ void shift_run_slow(const float4* __restrict__ src4, float4* __restrict__ dst4, int run0, int n_vec,
+                                            int rq, int o, int T4, float mean, float sd) {
+    const int lane = threadIdx.x & 31;
+    for (int t4 = run0 + lane; t4 < run0 + n_vec && t4 < T4; t4 += 32) {
+        int s = t4 + rq;
+        if (s >= T4) s -= T4;
+        const float4 a = __ldg(src4 + s);
+        const float4 c = __ldg(src4 + (s + 1 == T4 ? 0 : s + 1));
+        float4 x = a;
+        if (o == 1) x = make_float4(a.y, a.z, a.w, c.x);
+        if (o == 2) x = make_float4(a.z, a.w, c.x, c.y);
+        if (o == 3) x = make_float4(a.w, c.x, c.y, c.z);
+        if (NORM) x = norm4(x, mean, sd);
+        __stcs(dst4 + t4, x);
+    }
+}
+
+// Work counters of the persistent kernel: {next item, finished CTAs} per launch slot; the last CTA to finish clears
+// its slot, the host hands slots out round-robin (64 launches of one device can be in flight at a time).
+constexpr int kCtrSlots = 64;
+__device__ unsigned int g_stack_ctr[kCtrSlots][2];
+constexpr int kSegRuns = 4;            // consecutive runs of one row per work item (24 KB at VPT = 12)
+
+// what is fetched one item ahead of its use (two dependent table reads behind the atomic)
+struct RowMeta {
+    int mi, r_raw;
+    float mean, sd;
+};
+
+template <bool NORM, int THREADS, int VPT>
+__global__ void __maxnreg__(64) shift_stack_persist_kernel(
+    const float* __restrict__ mix, const int32_t* __restrict__ shifts, const int32_t* __restrict__ mix_index, int B, int M,
+    int T, float* __restrict__ out, const double* __restrict__ work, const int32_t* __restrict__ n_valid, int n_base, int N,
+    int slot) {
+    const int lane = threadIdx.x & 31;
+    const int T4 = T >> 2;
+    const int runs_per_row = (T4 + 32 * VPT - 1) / (32 * VPT);
+    const int segs_per_row = (runs_per_row + kSegRuns - 1) / kSegRuns;
+    int nv = N;
+    if (n_valid) {
+        const int left = __ldg(n_valid) - n_base;
+        nv = left < nv ? left : nv;
+    }
+    const unsigned total = nv > 0 ? (unsigned)nv * (unsigned)M * (unsigned)segs_per_row : 0u;
+    unsigned int* ctr = g_stack_ctr[slot];
+
+    auto grab = [&]() -> unsigned {
+        unsigned v = 0;
+        if (lane == 0) v = atomicAdd(ctr, 1u);
+        return __shfl_sync(0xffffffffu, v, 0);
+    };
+    auto fetch = [&](unsigned item, RowMeta& m) {
+        m.mi = -1;
+        if (item >= total) return;
+        const int row = (int)(item / (unsigned)segs_per_row);
+        const int n = row / M;
+        m.mi = mix_index ? __ldg(mix_index + n) : 0;
+        m.r_raw = __ldg(shifts + row);
+        if (NORM) {
+            const float2 ms = __ldg(reinterpret_cast<const float2*>(work + 2 * n));
+            m.mean = ms.x;
+            m.sd = ms.y;
+        } else {
+            m.mean = 0.f;
+            m.sd = 1.f;
+        }
+    };
+
+    unsigned item = grab();
+    RowMeta cur;
+    fetch(item, cur);
+    while (item < total) {
+        const unsigned item_n = grab();
+        RowMeta nxt;
+        fetch(item_n, nxt);
+        if (cur.mi >= 0 && cur.mi < B) {                       // stale / foreign table row: never read outside mix
+            const int row = (int)(item / (unsigned)segs_per_row);
+            const int seg = (int)(item - (unsigned)row * (unsigned)segs_per_row);
+            const int c = row % M;
+            const float4* src4 = reinterpret_cast<const float4*>(mix + ((size_t)cur.mi * M + c) * (size_t)T);
+            float4* dst4 = reinterpret_cast<float4*>(out + (size_t)row * T);
+            const int r = reduce_shift(cur.r_raw, T);
+            const int rq = r >> 2;
+            const int run_end = min(runs_per_row, (seg + 1) * kSegRuns);
+            const int o = r & 3;
+            for (int run = seg * kSegRuns; run < run_end; ++run) {
+                const int v0 = run * (32 * VPT);
+                int s0 = v0 + rq;
+                if (s0 >= T4) s0 -= T4;
+                if (s0 + 32 * VPT + 1 <= T4 && v0 + 32 * VPT <= T4) {
+                    const float4* p = src4 + s0 + lane;
+                    float4* q = dst4 + v0 + lane;
+                    switch (o) {
+                        case 0: shift_run_fast<NORM, 0, VPT>(p, q, lane, cur.mean, cur.sd); break;
+                        case 1: shift_run_fast<NORM, 1, VPT>(p, q, lane, cur.mean, cur.sd); break;
+                        case 2: shift_run_fast<NORM, 2, VPT>(p, q, lane, cur.mean, cur.sd); break;
+                        default: shift_run_fast<NORM, 3, VPT>(p, q, lane, cur.mean, cur.sd); break;
+                    }
+                } else {
+                    shift_run_slow<NORM>(src4, dst4, v0, 32 * VPT, rq, o, T4, cur.mean, cur.sd);
+                }
+            }
+        }
+        cur = nxt;
+        item = item_n;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ctr + 1, 1u) == gridDim.x - 1) {
+            ctr[0] = 0;
+            ctr[1] = 0;
+            __threadfence();
+        }
     }
 }
 
@@ -351,6 +529,18 @@ __global__ void __launch_bounds__(256) pcm16_to_f32_kernel(const short* __restri
         out[i] = (float)in[i] * (1.f / 32768.f);
 }
 
+constexpr int kPersistThreads = 512, kPersistVpt = 12;   // 16 warps x 64 registers = half of an SM's register file
+// resident CTAs of the persistent kernel (0 = the 256-thread kernel with one CTA per 16 KB of a row)
+int stack_persist_ctas() {
+    static const int v = [] {
+        const char* e = getenv("ASW_STACK");
+        if (!e || strncmp(e, "persist", 7) != 0) return 0;
+        const int n = e[7] == ':' ? atoi(e + 8) : 0;
+        return n > 0 ? n : kNumSms;
+    }();
+    return v;
+}
+
 template <bool NORM>
 int launch_rows(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int B, int M, int T, float* out,
                 const double* work, float* means, float* stds, cudaStream_t s, const int32_t* n_valid = nullptr,
@@ -367,7 +557,20 @@ int launch_rows(const float* mix, const int32_t* shifts, const int32_t* mix_inde
         const double* wk = work ? work + 2 * (size_t)n0 : nullptr;
         float* mu = means ? means + n0 : nullptr;
         float* sd = stds ? stds + n0 : nullptr;
-        if (vec) {
+        const int pctas = vec ? stack_persist_ctas() : 0;
+        constexpr int pvpt = kPersistVpt;
+        const long long items = (long long)nn * M * (((T / 4 + 32 * pvpt - 1) / (32 * pvpt) + kSegRuns - 1) / kSegRuns);
+        if (pctas > 0 && T / 4 >= 32 * pvpt && items < (1ll << 31)) {
+            // ASW_STACK=persist[:ctas]: one resident CTA per SM that leaves half of the register file to other streams
+            static std::atomic<unsigned> next_slot{0};
+            const int slot = (int)(next_slot.fetch_add(1) % kCtrSlots);
+            const int grid = (int)(items < pctas ? items : pctas);
+ASW_CARVE_ONCE((shift_stack_persist_kernel<NORM, kPersistThreads, kPersistVpt>));
+            shift_stack_persist_kernel<NORM, kPersistThreads, kPersistVpt><<<grid, kPersistThreads, 0, s>>>(
+                mix, sh, mi, B, M, T, o, wk, n_valid, n_base + n0, nn, slot);
+            ASW_LAUNCH_CHECK("shift_stack_persist_kernel");
+        } else if (vec) {
+            ASW_CARVE_ONCE(shift_stack_vec_kernel<NORM>);
             shift_stack_vec_kernel<NORM><<<grid, kThreads, 0, s>>>(mix, sh, mi, B, M, T, o, wk, mu, sd, n_valid, n_base + n0);
             ASW_LAUNCH_CHECK("shift_stack_vec_kernel");
         } else {
@@ -393,6 +596,7 @@ int launch_pcm16_to_f32(const short* in, float* out, size_t n, cudaStream_t s) {
         set_error("pcm16_to_f32: buffers must be 16-byte aligned");
         return ASW_ERR_ARG;
     }
+    ASW_CARVE_ONCE(pcm16_to_f32_kernel);
     pcm16_to_f32_kernel<<<kNumSms * 8, 256, 0, s>>>(in, out, n);
     ASW_LAUNCH_CHECK("pcm16_to_f32_kernel");
     return ASW_OK;

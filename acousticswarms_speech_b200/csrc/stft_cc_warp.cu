@@ -16,6 +16,8 @@
 // ncu on the first version (radix-4 x 5 through shared memory, 256 threads per FFT) showed 92 % L1/
 // shared throughput with 60 % of the shared wavefronts being bank-conflict replays; this version moves
 // 8x less data through shared memory per FFT and has no conflicts.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "fft32.cuh"
 
@@ -267,18 +269,29 @@ size_t warp_smem_bytes(int F) {
     return (size_t)M * (2 * 32 * 33) * sizeof(float) + (size_t)2 * M * F * sizeof(float2);
 }
 
+// ASW_STFT_CTAS=1: at most one CTA per SM (the request is padded past half of the shared memory), which leaves the
+// other half of the register file to a shift-stack CTA of another stream (shift_stack.cu, deep variant).
+int stft_cta_cap() {
+    static const int v = [] { const char* e = getenv("ASW_STFT_CTAS"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
 template <int M>
 int launch_t(const StftCcParams& p, cudaStream_t s) {
-    const size_t smem = warp_smem_bytes<M>(p.F);
+    size_t smem = warp_smem_bytes<M>(p.F);
+    const size_t half = 114 * 1024;
+    if (stft_cta_cap() == 1 && smem < half) smem = half;
     static PerDeviceOnce attr_once;
     if (attr_once.need()) {
+        const size_t most = stft_cta_cap() == 1 && warp_smem_bytes<M>(200) < half ? half : warp_smem_bytes<M>(200);
         ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_warp_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)warp_smem_bytes<M>(200)));
+                                            (int)most));
         // without this the driver may pick a carve-out that fits only one CTA (ncu: occupancy limit 1)
         // just enough shared memory for the resident CTAs, the rest stays L1
-        const int ctas = stft_cc_warp_ctas_per_sm(M);
-        int pct = (int)((ctas * (warp_smem_bytes<M>(200) + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
+        const int ctas = stft_cta_cap() == 1 ? 1 : stft_cc_warp_ctas_per_sm(M);
+        int pct = (int)((ctas * (most + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
         if (pct > 100) pct = 100;
+        if (carve_all()) pct = carve_all();
         ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_warp_kernel<M, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     dim3 grid(p.NG, p.Nw, p.B);

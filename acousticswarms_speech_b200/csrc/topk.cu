@@ -141,6 +141,7 @@ int launch_topk(const float* map, int B, int G, int K, int idx_offset, float* va
         set_error("topk: K=%d outside [1, %d]", K, kMaxK);
         return ASW_ERR_ARG;
     }
+    ASW_CARVE_ONCE(topk_kernel);
     topk_kernel<<<B, kThreads, 0, s>>>(map, G, K, idx_offset, val, idx);
     ASW_LAUNCH_CHECK("topk_kernel");
     return ASW_OK;

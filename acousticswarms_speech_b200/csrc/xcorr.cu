@@ -356,7 +356,7 @@ int asw_corr_create(asw_corr_t** out, int device, int M, int max_lag) {
     }
     DeviceGuard guard(device);      // the caller's current device is restored on return
     if (!guard.ok) {
-        set_error("cannot make device %d current", device);
+        set_error("cannot make CUDA device %d current (no CUDA device, or a bad index)", device);
         return ASW_ERR_CUDA;
     }
     asw_corr* h = new asw_corr();

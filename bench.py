@@ -236,9 +236,11 @@ class C2Pipeline:
         self.comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
         # priorities: the SM/latency-bound stages get SMs first, the HBM-bound shift-stack fills what is left
         three = args.streams == 3
-        self.stack_stream = torch.cuda.Stream(device=dev, priority=0) if three else None
+        stack_pri = int(os.environ.get("ASW_BENCH_STACK_PRIORITY", "0"))
+        score_pri = int(os.environ.get("ASW_BENCH_SCORE_PRIORITY", "-1"))
+        self.stack_stream = torch.cuda.Stream(device=dev, priority=stack_pri) if three else None
         self.prune_stream = torch.cuda.Stream(device=dev, priority=-1) if three else None
-        self.score_stream = torch.cuda.Stream(device=dev, priority=-1) if three else None
+        self.score_stream = torch.cuda.Stream(device=dev, priority=score_pri) if three else None
         self.serial = not three
         self.count_sync = bool(args.count_sync)
         self.mode = "plain"          # "plain" | "norm" (fused normalize_input from correlation tables) | "norm_exact"

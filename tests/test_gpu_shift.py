@@ -282,3 +282,18 @@ def test_fine_table_with_empty_candidate_slots(cuda_device):
     assert int(nt2[0]) == 7 and sh2[:7].tolist() == want_rows[:7]
     nothing = native.build_fine_table(cnt, off, root, torch.zeros_like(wid), own, 8)
     assert int(nothing[4][0]) == 0
+
+
+def test_persistent_variant_in_a_fresh_process(cuda_device):
+    """ASW_STACK=persist selects shift_stack_persist_kernel (one resident CTA per SM, shuffle realignment); the switch
+    is read once per process, so the bit-exact and normalize tests of this file are re-run in a child process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, ASW_STACK="persist")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_shift.py"), "-x", "-q", "-m", "gpu",
+                        "-k", "bit_exact or batched or full_size or shift_stack_norm"], env=env, cwd=root,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
