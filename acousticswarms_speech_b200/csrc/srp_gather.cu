@@ -320,6 +320,201 @@ __global__ void __launch_bounds__(kThreads, 1) srp_gather_bulk_kernel(SrpGatherP
     }
 }
 
+// ---- warp-specialised variant (round 2, second pass) -------------------------------------------------------------------
+// ncu's source view of srp_gather_bulk_kernel (profiles/r02_notes.md section 10): 81 % of the stage entries found the
+// stage's data not yet landed and 21 % of all warp samples sat in the `full` wait, although a stage's copies have a
+// whole stage of gathers (~30 us) to complete.  The copies were not slow, their ISSUE was: warp 0 walked the stage's
+// pairs serially (four dependent global loads per pair, a predicated single-lane copy per row) and then did a full
+// share of the gathers, so it was the last warp of every stage and the other 24 waited for it.  A further 7.5 % waited
+// for the per-pair range (rn / rlo) loads at the head of every pair.  Here
+//   * an extra PRODUCER warp does nothing but stage: a lane per pair (ranges and offsets loaded in parallel, the stage
+//     offsets by a warp scan), one cp.async.bulk per (pair, window) row, and it publishes {n, lo} of every staged pair
+//     in shared memory next to the data (released by the same mbarrier arrive);
+//   * the kThreads gather threads never touch the plan in global memory inside the pair loop.
+// Same arithmetic in the same order as the other two kernels: bit-identical maps.
+constexpr int kMaxStagePairs = kMaxMics * (kMaxMics - 1) / 2;
+
+template <int GPT, int kThreads>
+__global__ void __launch_bounds__(kThreads + 32, 1) srp_gather_ws_kernel(SrpGatherParams p, int ntiles, int n_items) {
+    extern __shared__ __align__(128) float s_tab[];
+    __shared__ uint64_t s_full[2], s_empty[2];
+    __shared__ int2 s_desc[2][kMaxStagePairs];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kThreads / 32;                 // gather warps; warp kWarps is the producer
+    if (tid == 0) {
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        mbar_init(&s_empty[0], kWarps);
+        mbar_init(&s_empty[1], kWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto groups_of = [&](int item) { const int t = item % ntiles; return p.tile_grp[t + 1] - p.tile_grp[t] - 1; };
+    auto advance = [&](StageCursor c) {
+        if (c.grp + 1 < groups_of(c.item)) {
+            ++c.grp;
+        } else if (c.w0 + kWc < p.Nw) {
+            c.w0 += kWc;
+            c.grp = 0;
+        } else {
+            c.item += gridDim.x;
+            c.w0 = 0;
+            c.grp = 0;
+        }
+        return c;
+    };
+    StageCursor cur{(int)blockIdx.x, 0, 0};
+    if (cur.item >= n_items) return;
+
+    if (warp == kWarps) {
+        // ---------------- producer ----------------
+        for (int s = 0; cur.item < n_items; ++s, cur = advance(cur)) {
+            const int bufi = s & 1;
+            // the buffer was last read by stage s - 2: every gather warp has arrived on its `empty` barrier
+            if (s >= 2) mbar_wait(&s_empty[bufi], (uint32_t)(((s - 2) >> 1) & 1));
+            const int b = cur.item / ntiles, t = cur.item % ntiles;
+            const float* gcc_b = p.gcc + (size_t)b * p.tab_len * p.Nw;
+            const int* rlo = p.rng_lo + (size_t)t * p.P;
+            const int* rn = p.rng_n + (size_t)t * p.P;
+            const int* gb = p.grp_flat + p.tile_grp[t];
+            const int wc = min(kWc, p.Nw - cur.w0);
+            const int p0 = gb[cur.grp], p1 = gb[cur.grp + 1];
+            float* buf = s_tab + bufi * p.stage_floats;
+            int carry = 0;
+            for (int base = p0; base < p1; base += 32) {
+                const int pp = base + lane;
+                const bool valid = pp < p1;
+                int n = 0, lo = 0, npd = 0, off = 0;
+                if (valid) { n = rn[pp]; lo = rlo[pp]; npd = p.npad[pp]; off = p.off[pp]; }
+                int incl = wc * n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const int so = carry + incl - wc * n;
+                if (valid) {
+                    s_desc[bufi][pp - p0] = make_int2(n, lo);
+                    const float* src = gcc_b + (size_t)p.Nw * off + (size_t)cur.w0 * npd + lo;
+                    for (int w = 0; w < wc; ++w)
+                        bulk_load(buf + so + w * n, src + (size_t)w * npd, (uint32_t)n * 4u, &s_full[bufi]);
+                }
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            __syncwarp();   // every lane's descriptors are written before lane 0's releasing arrive
+            if (lane == 0) mbar_expect_tx(&s_full[bufi], (uint32_t)carry * 4u);
+        }
+        return;
+    }
+
+    // ---------------- gather warps ----------------
+    bool on[GPT];
+    float best[GPT];
+    float acc[kWc][GPT];
+    for (int s = 0; cur.item < n_items; ++s) {
+        const StageCursor nxt = advance(cur);
+        const int bufi = s & 1;
+        const int b = cur.item / ntiles, t = cur.item % ntiles;
+        const int g_base = t * p.tile;
+        const int* gb = p.grp_flat + p.tile_grp[t];
+        const int n_groups = p.tile_grp[t + 1] - p.tile_grp[t] - 1;
+        const int wc = min(kWc, p.Nw - cur.w0);
+        if (cur.grp == 0) {
+            if (cur.w0 == 0) {
+#pragma unroll
+                for (int gi = 0; gi < GPT; ++gi) {
+                    const int sl = gi * kThreads + tid;
+                    on[gi] = sl < p.tile && g_base + sl < p.G;
+                    best[gi] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < kWc; ++w)
+#pragma unroll
+                for (int gi = 0; gi < GPT; ++gi) acc[w][gi] = 0.f;
+        }
+        const float* s_cur = s_tab + bufi * p.stage_floats;
+        const int p0 = gb[cur.grp], pp_end = gb[cur.grp + 1];
+        // lag positions of the first pair before the wait for the stage, those of pair pp + 1 while pair pp is gathered
+        uint32_t qn[GPT];
+#pragma unroll
+        for (int gi = 0; gi < GPT; ++gi)
+            qn[gi] = on[gi] ? __ldg(p.pos + (size_t)p0 * p.Gpad + g_base + gi * kThreads + tid) : 0u;
+        mbar_wait(&s_full[bufi], (uint32_t)((s >> 1) & 1));
+        int sm_off = 0;
+        for (int pp = p0; pp < pp_end; ++pp) {
+            const int2 d = s_desc[bufi][pp - p0];
+            const int n = d.x, lo = d.y;
+            uint32_t qc[GPT];
+#pragma unroll
+            for (int gi = 0; gi < GPT; ++gi) {
+                qc[gi] = qn[gi];
+                if (pp + 1 < pp_end && on[gi]) qn[gi] = __ldg(p.pos + (size_t)(pp + 1) * p.Gpad + g_base + gi * kThreads + tid);
+            }
+#pragma unroll
+            for (int gi = 0; gi < GPT; ++gi) {
+                if (!on[gi]) continue;
+                const uint32_t q = qc[gi];
+                const int i0 = (int)(q >> kFracBits);
+                const float f = (float)(q & ((1u << kFracBits) - 1)) * (1.0f / (float)(1 << kFracBits));
+                // 4-tap Lagrange weights for nodes -1, 0, 1, 2 (same expressions as srp_gather_kernel: same bits)
+                const float fm1 = f - 1.f, fm2 = f - 2.f, fp1 = f + 1.f;
+                const float c0 = -(1.f / 6.f) * f * fm1 * fm2;
+                const float c1 = 0.5f * fp1 * fm1 * fm2;
+                const float c2 = -0.5f * fp1 * f * fm2;
+                const float c3 = (1.f / 6.f) * fp1 * f * fm1;
+                const float* tp = s_cur + sm_off + (i0 - lo) - 1;
+#pragma unroll
+                for (int w = 0; w < kWc; ++w) {
+                    if (w < wc) {
+                        float v = c0 * tp[0];
+                        v = fmaf(c1, tp[1], v);
+                        v = fmaf(c2, tp[2], v);
+                        v = fmaf(c3, tp[3], v);
+                        acc[w][gi] += v;
+                        tp += n;
+                    }
+                }
+            }
+            sm_off += wc * n;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[bufi]);              // this warp is done reading the stage
+        if (cur.grp == n_groups - 1) {
+#pragma unroll
+            for (int w = 0; w < kWc; ++w)
+                if (w < wc) {
+#pragma unroll
+                    for (int gi = 0; gi < GPT; ++gi) best[gi] = fmaxf(best[gi], acc[w][gi]);
+                }
+            if (cur.w0 + kWc >= p.Nw) {
+#pragma unroll
+                for (int gi = 0; gi < GPT; ++gi) {
+                    const int slot = g_base + gi * kThreads + tid;
+                    if (on[gi]) p.map[(size_t)b * p.G + p.perm[slot]] = best[gi];
+                }
+            }
+        }
+        cur = nxt;
+    }
+}
+
+template <int GPT, int kThreads>
+int launch_ws_t(const SrpGatherParams& p, cudaStream_t s) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(srp_gather_ws_kernel<GPT, kThreads>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kSmemBudget));
+    }
+    const int ntiles = (p.G + p.tile - 1) / p.tile;
+    const long long items = (long long)ntiles * p.B;
+    const int grid = (int)(items < kNumSms ? items : kNumSms);
+    srp_gather_ws_kernel<GPT, kThreads><<<grid, kThreads + 32, 2 * (size_t)p.stage_floats * sizeof(float), s>>>(p, ntiles, (int)items);
+    ASW_LAUNCH_CHECK("srp_gather_ws_kernel");
+    return ASW_OK;
+}
+
 template <int GPT, int kThreads>
 int launch_bulk_t(const SrpGatherParams& p, cudaStream_t s) {
     static PerDeviceOnce attr_once;
@@ -355,6 +550,7 @@ int launch_t(const SrpGatherParams& p, cudaStream_t s) {
 // 3 rounds of 50 us  =>  fixed cost ~32 us = ~2850 hypercubes; tiles above 2048 use the 3-per-thread variant.
 constexpr int kThreads3 = 800;                  // 3 hypercubes per thread need ~80 registers: 25 warps per CTA
 constexpr int kMaxTile = 3 * kThreads3;
+constexpr int kWsThreads = kMaxThreads - 32;   // gather threads of the warp-specialised kernel (+ one producer warp)
 
 int choose_tile(int G, int B, int P, int tab_len) {
     const int kMinTile = 512;
@@ -396,9 +592,21 @@ int launch_srp_gather(const SrpGatherParams& p, cudaStream_t s) {
         if (p.tile > kMaxThreads) return launch_t<2, kMaxThreads>(p, s);
         return launch_t<1, kMaxThreads>(p, s);
     }
-    if (p.tile > 2 * kMaxThreads) return launch_bulk_t<3, kThreads3>(p, s);
-    if (p.tile > kMaxThreads) return launch_bulk_t<2, kMaxThreads>(p, s);
-    return launch_bulk_t<1, kMaxThreads>(p, s);
+    // ASW_GATHER=bulk: the first persistent kernel (warp 0 stages AND gathers), kept for A/B measurements
+    static const bool bulk = [] { const char* e = getenv("ASW_GATHER"); return e && strcmp(e, "bulk") == 0; }();
+    if (bulk) {
+        if (p.tile > 2 * kMaxThreads) return launch_bulk_t<3, kThreads3>(p, s);
+        if (p.tile > kMaxThreads) return launch_bulk_t<2, kMaxThreads>(p, s);
+        return launch_bulk_t<1, kMaxThreads>(p, s);
+    }
+    if (p.P > kMaxStagePairs) {
+        set_error("srp_gather: %d pairs exceed the stage descriptor table (%d)", p.P, kMaxStagePairs);
+        return ASW_ERR_RANGE;
+    }
+    // kWsThreads gather threads + the producer warp = 1024 threads
+    if (p.tile > 2 * kWsThreads) return launch_ws_t<3, kThreads3>(p, s);
+    if (p.tile > kWsThreads) return launch_ws_t<2, kWsThreads>(p, s);
+    return launch_ws_t<1, kWsThreads>(p, s);
 }
 
 }  // namespace asw
