@@ -17,6 +17,7 @@
 // shared throughput with 60 % of the shared wavefronts being bank-conflict replays; this version moves
 // 8x less data through shared memory per FFT and has no conflicts.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "fft32.cuh"
@@ -205,6 +206,178 @@ __global__ void stft_cc_warp_kernel(StftCcParams p) {
     }
 }
 
+// ---- round-robin variant of the fused kernel (M <= 8) ----------------------------------------------------------------
+// ncu's source view of stft_cc_warp_kernel<7, false> (profiles/r02_notes.md section 10): 15 % of all warp samples sit at
+// the __syncthreads between the seven FFTs of a frame and its pair products.  Two causes: seven warps per CTA spread
+// over four sub-partitions as 2/2/2/1 (two resident CTAs: 4/4/3/3), so the FFTs of the fuller partitions finish last
+// every frame; and the barrier makes every warp wait for the slowest FFT of the CURRENT frame.  Here
+//   * the CTA has eight warps whatever M is and the (frame, mic) FFTs of its frame group are dealt round-robin,
+//     task t = frame * M + mic to warp t mod 8: four warps per sub-partition, 8/M frames per round;
+//   * the block barrier is replaced by two pairs of alternating mbarriers.  `full`: a warp arrives (non-blocking) once
+//     its spectrum of round r is in the ring and waits for round r - 1 only AFTER the FFT of round r, just before the
+//     pair products of the frames that round r - 1 completed.  `read`: a warp arrives when its pair products of round
+//     r are done, and waits for round r - 1 just before it writes the spectrum of round r into the ring.  Either way a
+//     warp blocks only if some other warp is a whole FFT behind;
+//   * the spectra go through a ring of K frames, K the smallest depth for which a frame's slot is rewritten two rounds
+//     after the round that completed it (M = 7: 4), i.e. after the round in which it was read.
+// The FFTs and the order of the frame sums are those of stft_cc_warp_kernel: same bits.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rr_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void rr_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void rr_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
+constexpr int kRrWarps = 8;
+__host__ __device__ constexpr int rr_ring(int M) {   // smallest K with floor(M (f + K) / 8) >= floor((M f + M - 1) / 8) + 2 for all f
+    return M == 2 ? 8 : M == 3 ? 6 : M == 8 ? 2 : 4;
+}
+
+template <int M>
+__global__ void stft_cc_rr_kernel(StftCcParams p) {
+    constexpr int kP = M * (M - 1) / 2;
+    constexpr int K = rr_ring(M);
+    extern __shared__ __align__(16) float smem[];
+    __shared__ uint64_t s_full[2], s_read[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+    float* tile = smem + warp * (2 * 32 * 33);
+    c64* s_px = reinterpret_cast<c64*>(smem + kRrWarps * (2 * 32 * 33));   // [K][M][F]
+    float2* s_post = reinterpret_cast<float2*>(s_px + (size_t)K * M * p.F);   // [F] exp(-i pi k / 1024) of the scored bins
+    float2* s_seed = s_post + p.F;                                           // [4][32] W_1024^{lane j}, j = 1, 8, 16, 24
+    const int grp = blockIdx.x, w = blockIdx.y, b = blockIdx.z;
+    const int F = p.F;
+    if (tid == 0) {
+        rr_mbar_init(&s_full[0], kRrWarps);
+        rr_mbar_init(&s_full[1], kRrWarps);
+        rr_mbar_init(&s_read[0], kRrWarps);
+        rr_mbar_init(&s_read[1], kRrWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // twiddles live in shared memory, not in registers and not behind __ldg: the register file is full (64 data +
+    // 2 (M choose 2) sums) and the L1 left next to two CTAs' shared memory is 28 KB
+    for (int i = tid; i < F; i += 32 * kRrWarps) s_post[i] = __ldg(p.twpost + i);
+    if (tid < 128) {
+        const int j = tid >> 5, mult = j == 0 ? 1 : 8 * j;
+        s_seed[tid] = __ldg(p.tw1024 + ((mult * (tid & 31)) & 1023));
+    }
+    __syncthreads();
+
+    c64 acc[kP];
+#pragma unroll
+    for (int q = 0; q < kP; ++q) acc[q] = pk(0.f, 0.f);
+
+    const int n0 = grp * p.FG;
+    const int nfr = min(p.Nf, n0 + p.FG) - n0;
+    const int total = nfr * M, rounds = (total + kRrWarps - 1) / kRrWarps;
+    const float* xw = p.mix + (size_t)b * p.M * (size_t)p.T + (size_t)w * p.step;
+    auto prefetch_task = [&](int t) {
+        const int fr = t / M, m = t - fr * M;
+        prefetch_frame_n(tile, xw + (size_t)m * p.T, n0 + fr, p.win_len, lane);
+    };
+
+    if (warp < total) prefetch_task(warp);
+    for (int r = 0; r <= rounds; ++r) {     // round `rounds`: only the pair products of the last round's frames
+        const int t = r * kRrWarps + warp;
+        if (t < total) {
+            c64 v[32];
+            cp_async_wait_all();
+            __syncwarp();
+            {
+                const c64* raw = reinterpret_cast<const c64*>(tile);
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = raw[32 * q + lane];
+            }
+            __syncwarp();
+            dft32(v);
+            {
+                // opaque per round: otherwise the 28 products of the twiddle recurrence (a function of the lane only) are
+                // hoisted out of the round loop and kept in LOCAL memory -- 224 bytes per thread that the 28 KB of L1
+                // left next to two CTAs' shared memory cannot hold
+                float2 a1 = s_seed[lane], a8 = s_seed[32 + lane], a16 = s_seed[64 + lane], a24 = s_seed[96 + lane];
+                asm volatile("" : "+f"(a1.x), "+f"(a1.y), "+f"(a8.x), "+f"(a8.y), "+f"(a16.x), "+f"(a16.y), "+f"(a24.x), "+f"(a24.y));
+                twiddle_and_transpose(v, tile, lane, a1, a8, a16, a24);
+            }
+            __syncwarp();
+            load_transposed(v, tile, lane);
+            __syncwarp();
+            if (t + kRrWarps < total) prefetch_task(t + kRrWarps);
+            dft32(v);
+            // the ring slot of this frame was last read in round <= r - 1 (rr_ring): every warp has left those reads
+            if (r >= 1) rr_mbar_wait(&s_read[(r - 1) & 1], (uint32_t)(((r - 1) >> 1) & 1));
+            const int fr = t / M, m = t - fr * M;
+            c64* px = s_px + ((size_t)(fr % K) * M + m) * F;
+            const float tol2 = p.tol * p.tol;
+            const int partner = (32 - lane) & 31;
+            // opaque per round: otherwise the seven (bin index, twiddle address, slot address) triples are hoisted out
+            // of the round loop and spilled around every FFT (the register file is full: 64 data + 2 (M choose 2) sums)
+            int bin0 = p.bin0;
+            asm volatile("" : "+r"(bin0));
+#pragma unroll
+            for (int k2 = 0; k2 < kK2; ++k2) {
+                const int k = lane + 32 * k2;
+                const float2 zk = upk(v[bitrev5(k2)]);
+                const float2 give = upk(v[bitrev5(31 - k2)]);
+                float2 zc = make_float2(__shfl_sync(0xffffffffu, give.x, partner),
+                                        __shfl_sync(0xffffffffu, give.y, partner));
+                if (lane == 0) zc = upk(v[bitrev5((32 - k2) & 31)]);
+                const int f = k - bin0;
+                if (f >= 0 && f < F) {
+                    const float2 post = s_post[f];
+                    const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+                    const float2 o = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+                    const float2 Xf = cadd(e, cmul(post, o));
+                    const float n2 = fmaxf(fmaf(Xf.x, Xf.x, Xf.y * Xf.y), tol2);
+                    float inv;
+                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(n2));
+                    px[f] = pk(Xf.x * inv, Xf.y * inv);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && r < rounds) rr_mbar_arrive(&s_full[r & 1]);   // this warp's spectrum of round r is in the ring
+        if (r >= 1) {
+            // round r - 1 is complete for every warp (they have had one FFT of slack to get there)
+            rr_mbar_wait(&s_full[(r - 1) & 1], (uint32_t)(((r - 1) >> 1) & 1));
+            // frames completed by round r - 1 and not by round r - 2 (recomputed, not carried: no register to spare)
+            const int cnt = min(nfr, (kRrWarps * r) / M);
+            for (int fdone = min(nfr, (kRrWarps * (r - 1)) / M); fdone < cnt; ++fdone) {
+                if (tid < F) {
+                    const c64* px = s_px + (size_t)(fdone % K) * M * F + tid;
+                    float2 a[M];
+#pragma unroll
+                    for (int mm = 0; mm < M; ++mm) a[mm] = upk(px[mm * F]);
+                    int q = 0;
+#pragma unroll
+                    for (int ii = 0; ii < M; ++ii) {
+                        const c64 ai = pk(a[ii].x, a[ii].y), ai_rot = pk(a[ii].y, -a[ii].x);
+#pragma unroll
+                        for (int jj = ii + 1; jj < M; ++jj) {
+                            const c64 u = fma2(ai, pk(a[jj].x, a[jj].x), mul2(ai_rot, pk(a[jj].y, a[jj].y)));
+                            acc[q] = add2(acc[q], u);
+                            ++q;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && r < rounds) rr_mbar_arrive(&s_read[r & 1]);   // this warp's reads of round r are done
+    }
+    float2* cc_out = p.cc_part + ((((size_t)b * p.Nw + w) * p.NG + grp) * (size_t)F) * p.P;
+    if (tid < F) {
+#pragma unroll
+        for (int q = 0; q < kP; ++q) cc_out[(size_t)q * F + tid] = upk(acc[q]);
+    }
+}
+
 // Cross-spectra from the stored spectra (split path).  The M(M-1)/2 pairs are covered by tiles of 4 first mics x 8
 // second mics (i in [i0, i0+4), j in [j0, j0+8), j0 = i0, i0+8, ...): a thread owns one bin, keeps the tile's 32
 // accumulators in registers and loads 12 spectra per frame.  CTA = (frame group, window, mixture x tile).
@@ -300,6 +473,31 @@ int launch_t(const StftCcParams& p, cudaStream_t s) {
     return ASW_OK;
 }
 
+template <int M>
+size_t rr_smem_bytes(int F) {
+    return (size_t)kRrWarps * (2 * 32 * 33) * sizeof(float) + (size_t)rr_ring(M) * M * F * sizeof(float2) +
+           (size_t)(F + 128) * sizeof(float2);
+}
+
+template <int M>
+int launch_rr_t(const StftCcParams& p, cudaStream_t s) {
+    const size_t smem = rr_smem_bytes<M>(p.F);
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
+        const size_t most = rr_smem_bytes<M>(200);
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_rr_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+        // two CTAs per SM (16 warps at 128 registers fill the register file): shared memory for both, the rest stays L1
+        int pct = (int)((2 * (most + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
+        if (pct > 100) pct = 100;
+        if (carve_all()) pct = carve_all();
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(stft_cc_rr_kernel<M>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
+    dim3 grid(p.NG, p.Nw, p.B);
+    stft_cc_rr_kernel<M><<<grid, 32 * kRrWarps, smem, s>>>(p);
+    ASW_LAUNCH_CHECK("stft_cc_rr_kernel");
+    return ASW_OK;
+}
+
 }  // namespace
 
 bool stft_cc_warp_supported(const StftCcParams& p) {
@@ -353,6 +551,27 @@ int launch_stft_split(const StftCcParams& p, cudaStream_t s) {
 }
 
 int launch_stft_cc_warp(const StftCcParams& p, cudaStream_t s) {
+    // Round-robin kernel for M <= 7 (C2, 64 mixtures of 7 mics: 455 -> 410 us; M = 2 .. 6: 5 - 15 % faster); M = 8 deals
+    // one frame per round either way and its 28 pair sums leave the round-robin bookkeeping no registers (measured
+    // 2 % slower), so it keeps the first kernel.  ASW_STFT=classic / rr force one kernel for A/B measurements and
+    // the bit-identity test.
+    static const int force = [] {
+        const char* e = getenv("ASW_STFT");
+        return !e ? 0 : strcmp(e, "classic") == 0 ? 1 : strcmp(e, "rr") == 0 ? 2 : 0;
+    }();
+    const bool rr = force == 2 || (force == 0 && p.M <= 7);
+    if (rr && stft_cta_cap() != 1) {
+        switch (p.M) {
+            case 2: return launch_rr_t<2>(p, s);
+            case 3: return launch_rr_t<3>(p, s);
+            case 4: return launch_rr_t<4>(p, s);
+            case 5: return launch_rr_t<5>(p, s);
+            case 6: return launch_rr_t<6>(p, s);
+            case 7: return launch_rr_t<7>(p, s);
+            case 8: return launch_rr_t<8>(p, s);
+            default: break;
+        }
+    }
     switch (p.M) {
         case 2: return launch_t<2>(p, s);
         case 3: return launch_t<3>(p, s);

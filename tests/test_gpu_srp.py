@@ -230,3 +230,27 @@ def test_fs_44100(cuda_device):
     want = srp_oracle.score(mix, geo.grids, scene.mic_positions, freq_bins, 44100, n_fft)
     assert len(srp_oracle.window_starts(T, 36000)) == 6
     assert np.abs(got - want).max() <= TOL * want.max()
+
+
+def test_kernel_variants_bit_identical(cuda_device, tmp_path):
+    """The scoring kernels have measured alternatives kept for A/B runs: the fused STFT with a block barrier per frame
+    (ASW_STFT=classic) vs the round-robin / mbarrier kernel, and the gather whose warp 0 stages and gathers
+    (ASW_GATHER=bulk) or the cp.async ring (legacy) vs the warp-specialised kernel.  Every variant does the same
+    arithmetic in the same order: maps and cross-spectra must be equal bit for bit (3 .. 8 mics, ragged tail, batches)."""
+    import os
+    import subprocess
+    import sys
+    from _variant_worker import variant_maps
+    mine = variant_maps()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for env_add in ({"ASW_STFT": "classic", "ASW_GATHER": "bulk"}, {"ASW_STFT": "rr", "ASW_GATHER": "legacy"}):
+        path = str(tmp_path / ("variant_" + env_add["ASW_STFT"] + ".npz"))
+        env = dict(os.environ, **env_add)
+        env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+        r = subprocess.run([sys.executable, os.path.join(root, "tests", "_variant_worker.py"), path], env=env, cwd=root,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+        other = np.load(path)
+        assert set(other.files) == set(mine)
+        for k in mine:
+            assert np.array_equal(mine[k], other[k]), (env_add, k)
