@@ -131,18 +131,37 @@ __global__ void __launch_bounds__(32 * kFftWarps, 5) gcc_fft_kernel(GccParams p)
     __syncthreads();
     if (pr >= p.P) return;                                               // whole warp exits together
 
-    for (int f = lane; f < F; f += 32) {
-        const float2* src = p.cc_part + ((((size_t)b * p.Nw + w) * p.NG) * (size_t)p.P + pr) * F + f;
-        float2 s = make_float2(0.f, 0.f);
+    {
+        // frame-group partial sums of this curve's spectrum: all bins of a lane (<= 8) are loaded together for every
+        // group, four groups in flight (the first version walked bins x groups one dependent load at a time: a third of
+        // the kernel's samples sat on those loads); same order of additions per bin
+        constexpr int kBinsPerLane = kMaxBins / 32;
+        const float2* src = p.cc_part + ((((size_t)b * p.Nw + w) * p.NG) * (size_t)p.P + pr) * F;
+        const size_t gstride = (size_t)F * p.P;
+        float2 sum[kBinsPerLane];
+#pragma unroll
+        for (int i = 0; i < kBinsPerLane; ++i) sum[i] = make_float2(0.f, 0.f);
+#pragma unroll 4
         for (int g = 0; g < p.NG; ++g) {
-            const float2 v = src[(size_t)g * F * p.P];
-            s.x += v.x;
-            s.y += v.y;
+#pragma unroll
+            for (int i = 0; i < kBinsPerLane; ++i) {
+                const int f = lane + 32 * i;
+                if (f < F) {
+                    const float2 v = src[(size_t)g * gstride + f];
+                    sum[i].x += v.x;
+                    sum[i].y += v.y;
+                }
+            }
         }
-        s.x *= p.inv_nf;
-        s.y *= p.inv_nf;
-        if (p.cc_out) p.cc_out[(((size_t)b * p.Nw + w) * F + f) * p.P + pr] = s;
-        s_x[f] = s;
+#pragma unroll
+        for (int i = 0; i < kBinsPerLane; ++i) {
+            const int f = lane + 32 * i;
+            if (f < F) {
+                const float2 sc = make_float2(sum[i].x * p.inv_nf, sum[i].y * p.inv_nf);
+                if (p.cc_out) p.cc_out[(((size_t)b * p.Nw + w) * F + f) * p.P + pr] = sc;
+                s_x[f] = sc;
+            }
+        }
     }
     __syncwarp();
 
@@ -195,6 +214,36 @@ __global__ void __launch_bounds__(32 * kFftWarps, 5) gcc_fft_kernel(GccParams p)
     __syncwarp();
 
     float* out = p.gcc + (size_t)b * p.tab_len * p.Nw + (size_t)p.Nw * p.off[pr] + (size_t)w * npd;
+    if (U == 4) {
+        // a lane per INTEGER lag: 12 shared loads feed the lag's four table entries (the first version did a lane per
+        // entry: 24 shared loads each), the weights stay in registers, one 16-byte store; same fma chains, same bits
+        float wt[3][kTaps];
+#pragma unroll
+        for (int fr = 0; fr < 3; ++fr)
+#pragma unroll
+            for (int t = 0; t < kTaps; ++t) wt[fr][t] = s_fir[fr * kTaps + t];
+        for (int j = lane; 4 * j < npd; j += 32) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * j < n) {
+                float r[kTaps];
+#pragma unroll
+                for (int t = 0; t < kTaps; ++t) r[t] = s_r1[j + t];
+                float v1 = 0.f, v2 = 0.f, v3 = 0.f;
+#pragma unroll
+                for (int t = 0; t < kTaps; ++t) {
+                    v1 = fmaf(wt[0][t], r[t], v1);
+                    v2 = fmaf(wt[1][t], r[t], v2);
+                    v3 = fmaf(wt[2][t], r[t], v3);
+                }
+                o.x = r[kMargin];
+                o.y = 4 * j + 1 < n ? v1 : 0.f;
+                o.z = 4 * j + 2 < n ? v2 : 0.f;
+                o.w = 4 * j + 3 < n ? v3 : 0.f;
+            }
+            *reinterpret_cast<float4*>(out + 4 * j) = o;    // npad, off and tab_len are multiples of 4 entries
+        }
+        return;
+    }
     for (int i = lane; i < npd; i += 32) {
         float val = 0.f;
         if (i < n) {
