@@ -13,9 +13,10 @@ from oracle import geometry_oracle
 def variant_maps():
     out = {}
     for n_mics, T, pad_tail, B in ((3, 48000, False, 2), (4, 50003, True, 1), (6, 96000, False, 3), (7, 96000, False, 5),
-                                   (8, 48000, False, 2)):
+                                   (8, 48000, False, 2), (32, 48000, False, 2)):
         scene = synth.small_scene(n_mics=n_mics, seed=2)
-        geo = geometry_oracle.GeometryOracle(scene.mic_positions, scene.roi, build_fine=False)
+        roi = scene.roi if n_mics <= 8 else [0.6, 0.9, -0.2, 0.1, 0.0, 0.2]     # 496 pairs: keep the grid small
+        geo = geometry_oracle.GeometryOracle(scene.mic_positions, roi, build_fine=False)
         lag = native.pair_lags(geo.grids, scene.mic_positions, scene.fs, 343.0)
         srp = native.NativeSRP(lag, n_mics, pad_tail=pad_tail)
         mix = np.stack([synth.mixture(scene, 2, T, seed=11 + b) for b in range(B)])

@@ -121,6 +121,19 @@ def test_generic_mic_count(cuda_device):
     assert np.abs(got - want).max() <= TOL * want.max()
 
 
+def test_max_mic_count(cuda_device):
+    """32 mics = 496 pairs: the split STFT in four chunks of eight mics, 20 pair tiles, gather stages of more than 32
+    pairs (the producer warp's second lane round) and the full stage-descriptor table."""
+    scene = synth.table_array(32, np.random.default_rng(9))
+    scene.roi = [2.0, 2.6, 3.2, 3.8, 0.0, 0.4]                 # where the speakers stand
+    geo = geometry_oracle.GeometryOracle(scene.mic_positions, [2.1, 2.4, 3.3, 3.6, 0.0, 0.2], build_fine=False)
+    mix = synth.mixture(scene, 2, 48000, seed=3)
+    srp = _native(scene, geo.grids)
+    got = srp.score(torch.from_numpy(mix).cuda(), 24000).cpu().numpy()[0]
+    want = srp_oracle.score(mix, geo.grids, scene.mic_positions, freq_bins, scene.fs, n_fft)
+    assert np.abs(got - want).max() <= TOL * want.max()
+
+
 @pytest.mark.parametrize("n_mics,T", [(4, 48000), (4, 96000), (4, 50003), (10, 48000)])
 def test_tail_padded_frame_mode(cuda_device, small, n_mics, T):
     """ASW_FRAMES_PAD_TAIL (the other reading of assumption A1): ceil((win - nfft) / hop) + 1 frames, the ragged
