@@ -17,6 +17,8 @@ def run(tag, M, T, B, fs=48000):
     node = SRP_PHAT(scene.mic_positions, freq_bins, scene.roi, FS=fs, n_fft=n_fft, grid_size=0.05,
                     threshold=list(SRP_THRESHOLDS), WIDTH=8, device=dev)
     h = node.native
+    if os.environ.get('STFT_PATH'):
+        h.set_stft_path(os.environ['STFT_PATH'])      # 'split': FFT + PHAT to global memory, then the pair-product kernel
     nb = min(B, 4)
     base = torch.from_numpy(synth.mixtures(scene, 3, T, seeds=list(range(200, 200 + nb)))).to(dev)
     mix = torch.cat([torch.roll(base, shifts=i, dims=2) for i in range((B + nb - 1) // nb)], 0)[:B].contiguous()
@@ -30,7 +32,7 @@ def run(tag, M, T, B, fs=48000):
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     sha = hashlib.sha256(tabs.cpu().numpy().tobytes()).hexdigest()[:16]
-    print(f"{os.environ.get('ASW_STFT', 'rr'):7s} {tag}: M={M} B={B} T={T} transform {best * 1e3:.1f} us  tables sha {sha}", flush=True)
+    print(f"{os.environ.get('ASW_STFT', 'rr'):7s} {os.environ.get('STFT_PATH', 'auto'):5s} {tag}: M={M} B={B} T={T} transform {best * 1e3:.1f} us  tables sha {sha}", flush=True)
 
 
 run("C2 B=64", 7, 144000, 64)
