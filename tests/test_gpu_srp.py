@@ -89,6 +89,23 @@ def test_short_signal_gives_zero_map(cuda_device, small):
     assert (got == 0).all()
 
 
+@pytest.mark.parametrize("n_mics", [3, 7, 8])
+@pytest.mark.parametrize("win", [2048, 2600, 3100, 6200])
+def test_few_frames_per_window(cuda_device, n_mics, win):
+    """Windows of 1, 2, 3 and 9 STFT frames: fewer (frame, mic) FFTs than the eight warps of the round-robin kernel, a
+    last round with idle warps, one partial frame group; M = 8 takes the warp-per-mic kernel."""
+    scene = synth.small_scene(n_mics=n_mics, seed=3)
+    geo = geometry_oracle.GeometryOracle(scene.mic_positions, scene.roi, build_fine=False)
+    srp = _native(scene, geo.grids)
+    T = 4 * win
+    mix = synth.mixture(scene, 2, T, seed=5)
+    assert srp.num_frames(win) == (win - n_fft) // (n_fft // 4) + 1
+    got = srp.score(torch.from_numpy(mix).cuda(), win).cpu().numpy()[0]
+    want = srp_oracle.score(mix, geo.grids, scene.mic_positions, freq_bins, scene.fs, n_fft, window=win)
+    assert want.max() > 0
+    assert np.abs(got - want).max() <= TOL * want.max()
+
+
 def test_silence_and_phat_floor(cuda_device, small):
     scene, geo = small
     srp = _native(scene, geo.grids)
