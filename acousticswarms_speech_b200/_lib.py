@@ -19,6 +19,7 @@ SYMBOLS = [
     "asw_build_shift_table", "asw_shift_stack_counted", "asw_pcm16_to_f32", "asw_patch_powers",
     "asw_srp_set_frame_mode", "asw_srp_num_frames_mode", "asw_select_set_grid1", "asw_srp_set_stft_path", "asw_srp_gcc", "asw_srp_gather",
     "asw_corr_create", "asw_corr_destroy", "asw_corr_table_len", "asw_corr_tables", "asw_shift_stack_norm_tab",
+    "asw_shift_stack_norm_grouped",
     "asw_build_fine_table",
 ]
 
@@ -84,6 +85,7 @@ def load():
     lib.asw_corr_table_len.argtypes = [vp]
     lib.asw_corr_tables.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.asw_shift_stack_norm_tab.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, i32, vp]
+    lib.asw_shift_stack_norm_grouped.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.asw_build_fine_table.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name, None)

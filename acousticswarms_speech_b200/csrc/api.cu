@@ -725,4 +725,16 @@ int asw_shift_stack_norm_tab(const float* mix_dev, const int32_t* shifts_dev, co
                                    work_dev, tables_dev, table_len, max_lag, n_valid_dev, n_base, (cudaStream_t)stream);
 }
 
+int asw_shift_stack_norm_grouped(const float* mix_dev, const int32_t* shifts_dev, const int32_t* mix_index_dev, int N, int B,
+                                 int M, int T, float* out_dev, float* means_dev, float* stds_dev, double* work_dev,
+                                 int32_t* ranges_dev, const int32_t* n_valid_dev, int n_base, void* stream) {
+    if (!mix_dev || !shifts_dev || !mix_index_dev || !out_dev || !means_dev || !stds_dev || !work_dev || !ranges_dev ||
+        N < 0 || B < 1 || M < 1 || M > kMaxMics || T < 2 || n_base < 0) {
+        set_error("asw_shift_stack_norm_grouped: null buffer or bad shape (N=%d B=%d M=%d T=%d)", N, B, M, T);
+        return ASW_ERR_ARG;
+    }
+    return launch_shift_stack_norm_grouped(mix_dev, shifts_dev, mix_index_dev, N, B, M, T, out_dev, means_dev, stds_dev,
+                                           work_dev, ranges_dev, n_valid_dev, n_base, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -155,5 +155,8 @@ int launch_shift_stack_counted(const float* mix, const int32_t* shifts, const in
 int launch_shift_stack_norm(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int B,
                             int M, int T, float* out, float* means, float* stds, double* work, const double* tables,
                             int table_stride, int max_lag, const int32_t* n_valid, int n_base, cudaStream_t s);
+int launch_shift_stack_norm_grouped(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int B, int M,
+                                    int T, float* out, float* means, float* stds, double* work, int32_t* ranges,
+                                    const int32_t* n_valid, int n_base, cudaStream_t s);
 
 }  // namespace asw

@@ -504,6 +504,179 @@ __global__ void __launch_bounds__(kStatThreads) shift_ref_stats_kernel(const flo
     }
 }
 
+// ---- statistics of a table whose rows are grouped by mixture ------------------------------------------------------------
+// The coarse stage stacks ~35 patches per mixture: the per-mixture correlation tables cost as much as the exact pass
+// they replace (13 - 18 us per mixture), and the exact pass reads a mixture's M T samples once PER PATCH through L2.
+// Here a CTA owns (mixture, time tile): it quantises the tile of all channels (plus a halo of kGrpHalo samples) into
+// shared memory ONCE and serves every patch of the mixture from it.  Both moments are sums of integers --
+//     s[t] = sum_c k_c[(t + d_c) mod T],  k = rint(x 2^15),  d_c = r_c - r_0 (a common shift leaves a circular sum alone),
+//     sum ref = sum_t s / (M 2^15),   sum ref^2 = sum_t s^2 / (M 2^15)^2  (s^2 < 2^38, the total < 2^56: exact in int64)
+// so any order of accumulation (warp reductions, shared and global atomics) gives the same bits, and the statistics are
+// those of the unrounded mic average (the per-patch pass rounds ref = fl(sum / M) to float first: 1e-8 relative apart).
+constexpr int kGrpThreads = 512, kGrpHalo = 512, kGrpTile = 2048, kGrpChunk = 128, kGrpMaxM = 8;
+
+__global__ void group_ranges_kernel(const int32_t* __restrict__ mix_index, const int32_t* __restrict__ n_valid, int n_base,
+                                    int N, int B, int32_t* __restrict__ start, unsigned long long* __restrict__ acc) {
+    const int nv = n_valid ? max(0, min(N, *n_valid - n_base)) : N;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nv) {
+        acc[2 * i] = 0ull;
+        acc[2 * i + 1] = 0ull;
+    }
+    if (i <= B) {                       // first row whose mixture index is >= i (rows are non-decreasing in mixture)
+        int lo = 0, hi = nv;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (mix_index[mid] < i) lo = mid + 1;
+            else hi = mid;
+        }
+        start[i] = lo;
+    }
+}
+
+template <int M>
+__global__ void __launch_bounds__(kGrpThreads, 2) shift_stats_grouped_kernel(const float* __restrict__ mix,
+                                                                            const int32_t* __restrict__ shifts,
+                                                                            const int32_t* __restrict__ start, int T,
+                                                                            unsigned long long* __restrict__ acc) {
+    extern __shared__ int s_q[];                               // [M][kGrpTile + 2 kGrpHalo] quantised samples
+    __shared__ int s_d[kGrpChunk][M];                          // relative shifts of the chunk's patches
+    __shared__ unsigned s_acc[kGrpChunk][4];                  // CTA sums: sum s (two's complement) and three 20-bit limbs of sum s^2
+    __shared__ int s_far[kGrpChunk];                           // some |d_c| exceeds the halo: read that patch from global
+    constexpr int kW = kGrpTile + 2 * kGrpHalo;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int n0 = start[b], n1 = start[b + 1];
+    if (n0 >= n1) return;
+    const int t0 = blockIdx.x * kGrpTile;
+    const int len = min(kGrpTile, T - t0);
+    const float* src = mix + (size_t)b * M * (size_t)T;
+    if (T >= kW) {                                             // the tile wraps at most once: no integer division
+        for (int c = 0; c < M; ++c) {
+            const float* row = src + (size_t)c * T;
+            int* dst = s_q + c * kW;
+#pragma unroll 6
+            for (int i = tid; i < len + 2 * kGrpHalo; i += kGrpThreads) {
+                int tt = t0 - kGrpHalo + i;
+                tt += tt < 0 ? T : 0;
+                tt -= tt >= T ? T : 0;
+                dst[i] = __float2int_rn(__ldg(row + tt) * 32768.f);
+            }
+        }
+    } else {
+        for (int c = 0; c < M; ++c)
+            for (int i = tid; i < len + 2 * kGrpHalo; i += kGrpThreads) {
+                int tt = (t0 - kGrpHalo + i) % T;
+                if (tt < 0) tt += T;
+                s_q[c * kW + i] = __float2int_rn(__ldg(src + (size_t)c * T + tt) * 32768.f);
+            }
+    }
+    for (int c0 = n0; c0 < n1; c0 += kGrpChunk) {
+        const int np = min(kGrpChunk, n1 - c0);
+        __syncthreads();                                       // tile ready / previous chunk flushed
+        for (int i = tid; i < np; i += kGrpThreads) {
+            const int32_t* sh = shifts + (size_t)(c0 + i) * M;
+            const int r0 = reduce_shift(sh[0], T);
+            int far = 0;
+#pragma unroll
+            for (int c = 0; c < M; ++c) {
+                int d = reduce_shift(sh[c], T) - r0;           // in (-T, T)
+                if (2 * d > T) d -= T;
+                if (2 * d < -T) d += T;
+                s_d[i][c] = d;
+                far |= (d < -kGrpHalo || d > kGrpHalo);
+            }
+            s_far[i] = far;
+            s_acc[i][0] = s_acc[i][1] = s_acc[i][2] = s_acc[i][3] = 0u;
+        }
+        __syncthreads();
+        for (int pi = 0; pi < np; ++pi) {
+            int a1 = 0;
+            long long a2 = 0;
+            if (!s_far[pi]) {
+                int base[M];
+#pragma unroll
+                for (int c = 0; c < M; ++c) base[c] = c * kW + kGrpHalo + s_d[pi][c] + tid;
+#pragma unroll
+                for (int k = 0; k < kGrpTile / kGrpThreads; ++k) {
+                    if (tid + k * kGrpThreads < len) {
+                        int sum = 0;
+#pragma unroll
+                        for (int c = 0; c < M; ++c) sum += s_q[base[c] + k * kGrpThreads];
+                        a1 += sum;
+                        a2 += (long long)sum * sum;
+                    }
+                }
+            } else {
+                for (int k = 0; k < kGrpTile / kGrpThreads; ++k) {
+                    const int i = tid + k * kGrpThreads;
+                    if (i < len) {
+                        int sum = 0;
+                        for (int c = 0; c < M; ++c) {
+                            int tt = (t0 + i + s_d[pi][c]) % T;
+                            if (tt < 0) tt += T;
+                            sum += __float2int_rn(__ldg(src + (size_t)c * T + tt) * 32768.f);
+                        }
+                        a1 += sum;
+                        a2 += (long long)sum * sum;
+                    }
+                }
+            }
+            // warp sums: |a1| < 2^22 per thread; a2 < 2^40 per thread, split into 20-bit limbs for the 32-bit redux
+            const int w1 = __reduce_add_sync(0xffffffffu, a1);
+            const unsigned long long u2 = (unsigned long long)a2;
+            const unsigned l0 = __reduce_add_sync(0xffffffffu, (unsigned)(u2 & 0xfffffull));
+            const unsigned l1 = __reduce_add_sync(0xffffffffu, (unsigned)((u2 >> 20) & 0xfffffull));
+            const unsigned l2 = __reduce_add_sync(0xffffffffu, (unsigned)(u2 >> 40));
+            if ((tid & 31) == 0) {        // native 32-bit shared atomics (a 64-bit shared atomicAdd is a CAS loop): the CTA
+                atomicAdd(&s_acc[pi][0], (unsigned)w1);   // sums stay below 2^31: |sum s| < 2^29, limbs < 16 warps x 2^25
+                atomicAdd(&s_acc[pi][1], l0);
+                atomicAdd(&s_acc[pi][2], l1);
+                atomicAdd(&s_acc[pi][3], l2);
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < np; i += kGrpThreads) {
+            atomicAdd(acc + 2 * (size_t)(c0 + i), (unsigned long long)(long long)(int)s_acc[i][0]);
+            atomicAdd(acc + 2 * (size_t)(c0 + i) + 1, (unsigned long long)s_acc[i][1] + ((unsigned long long)s_acc[i][2] << 20) +
+                                                          ((unsigned long long)s_acc[i][3] << 40));
+        }
+    }
+}
+
+__global__ void group_finalise_kernel(const int32_t* __restrict__ mix_index, const int32_t* __restrict__ n_valid, int n_base,
+                                      int N, int B, int M, int T, double* __restrict__ work, float* __restrict__ means,
+                                      float* __restrict__ stds) {
+    const int nv = n_valid ? max(0, min(N, *n_valid - n_base)) : N;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nv) return;
+    const int mi = mix_index[n];
+    if (mi < 0 || mi >= B) {                                   // stale table row: the per-patch pass's recognisable result
+        means[n] = 0.f;
+        stds[n] = 0.f;
+        *reinterpret_cast<float2*>(work + 2 * n) = make_float2(0.f, 0.f);
+        return;
+    }
+    const unsigned long long* acc = reinterpret_cast<const unsigned long long*>(work);
+    const long long a1 = (long long)acc[2 * n];
+    const unsigned long long a2 = acc[2 * n + 1];
+    const double scale = 1.0 / (32768.0 * (double)M);
+    finalise_stats((double)a1 * scale, (double)a2 * scale * scale, T, n, work, means, stds);
+}
+
+template <int M>
+int launch_grouped_t(const float* mix, const int32_t* shifts, const int32_t* start, int B, int T, double* work,
+                     cudaStream_t s) {
+    const size_t smem = (size_t)M * (kGrpTile + 2 * kGrpHalo) * sizeof(int);
+    static PerDeviceOnce attr_once;
+    if (attr_once.need())
+        ASW_CUDA_CHECK(cudaFuncSetAttribute(shift_stats_grouped_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((T + kGrpTile - 1) / kGrpTile, B);
+    shift_stats_grouped_kernel<M><<<grid, kGrpThreads, smem, s>>>(mix, shifts, start, T,
+                                                                  reinterpret_cast<unsigned long long*>(work));
+    ASW_LAUNCH_CHECK("shift_stats_grouped_kernel");
+    return ASW_OK;
+}
+
 // int16 PCM -> float32 in [-1, 1): x / 32768, the conversion soundfile/librosa apply when the reference loads
 // its PCM_16 wav files (sep/helpers/utils.py read_audio_file); exact in float32.
 __global__ void __launch_bounds__(256) pcm16_to_f32_kernel(const short* __restrict__ in, float* __restrict__ out,
@@ -623,6 +796,37 @@ int launch_shift_stack_norm(const float* mix, const int32_t* shifts, const int32
                                                                  table_stride, max_lag, n_valid, n_base);
     ASW_LAUNCH_CHECK("shift_ref_stats_kernel");
     return launch_rows<true>(mix, shifts, mix_index, N, B, M, T, out, work, means, stds, s, n_valid, n_base);
+}
+
+// Fused shift-stack + normalize_input for a table grouped by mixture (see shift_stats_grouped_kernel); M > 8 or a
+// null mix_index fall back to the per-patch pass.
+int launch_shift_stack_norm_grouped(const float* mix, const int32_t* shifts, const int32_t* mix_index, int N, int B, int M,
+                                    int T, float* out, float* means, float* stds, double* work, int32_t* ranges,
+                                    const int32_t* n_valid, int n_base, cudaStream_t s) {
+    if (N == 0) return ASW_OK;
+    if (M > kGrpMaxM || M < 2 || !mix_index || !ranges)
+        return launch_shift_stack_norm(mix, shifts, mix_index, N, B, M, T, out, means, stds, work, nullptr, 0, 0, n_valid,
+                                       n_base, s);
+    const int32_t* sh = shifts + (size_t)n_base * M;
+    const int32_t* mi = mix_index + n_base;
+    const int rows = N > B + 1 ? N : B + 1;
+    group_ranges_kernel<<<(rows + 255) / 256, 256, 0, s>>>(mi, n_valid, n_base, N, B, ranges,
+                                                           reinterpret_cast<unsigned long long*>(work));
+    ASW_LAUNCH_CHECK("group_ranges_kernel");
+    int rc = ASW_OK;
+    switch (M) {
+        case 2: rc = launch_grouped_t<2>(mix, sh, ranges, B, T, work, s); break;
+        case 3: rc = launch_grouped_t<3>(mix, sh, ranges, B, T, work, s); break;
+        case 4: rc = launch_grouped_t<4>(mix, sh, ranges, B, T, work, s); break;
+        case 5: rc = launch_grouped_t<5>(mix, sh, ranges, B, T, work, s); break;
+        case 6: rc = launch_grouped_t<6>(mix, sh, ranges, B, T, work, s); break;
+        case 7: rc = launch_grouped_t<7>(mix, sh, ranges, B, T, work, s); break;
+        default: rc = launch_grouped_t<8>(mix, sh, ranges, B, T, work, s); break;
+    }
+    if (rc != ASW_OK) return rc;
+    group_finalise_kernel<<<(N + 255) / 256, 256, 0, s>>>(mi, n_valid, n_base, N, B, M, T, work, means, stds);
+    ASW_LAUNCH_CHECK("group_finalise_kernel");
+    return launch_rows<true>(mix, sh, mi, N, B, M, T, out, work, means, stds, s, n_valid, n_base);
 }
 
 }  // namespace asw

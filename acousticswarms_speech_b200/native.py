@@ -536,12 +536,16 @@ class CorrTables:
         return tables[b, 2 * self.M + p * n: 2 * self.M + (p + 1) * n]
 
 
-def shift_stack_norm(mix, shifts, mix_index=None, out=None, tables=None, max_lag=0, n_total=None, n_base=0, N=None):
+def shift_stack_norm(mix, shifts, mix_index=None, out=None, tables=None, max_lag=0, n_total=None, n_base=0, N=None,
+                     grouped=False):
     """shift_stack fused with normalize_input (SpeakerLocalization/network.py:28-40).
     Returns (data_norm (N, M, T), means (N, 1, 1), stds (N, 1, 1)).
     ``tables`` (B, table_len) float64 from ``CorrTables.compute`` (+ its ``max_lag``): the statistics come from the
     per-mixture tables (asw_shift_stack_norm_tab) instead of a pass over every patch.
-    ``n_total`` (1,) int32 CUDA: rows [n_base, n_base + N) of a device-built table, rows >= n_total[0] skipped."""
+    ``n_total`` (1,) int32 CUDA: rows [n_base, n_base + N) of a device-built table, rows >= n_total[0] skipped.
+    ``grouped``: the rows are grouped by mixture (``mix_index`` non-decreasing, as the device-built tables are) and no
+    ``tables`` are given: one pass over each mixture's audio serves all of its patches (asw_shift_stack_norm_grouped,
+    exact integer statistics) -- the choice for a few dozen patches per mixture."""
     if mix.dim() == 2:
         mix = mix.unsqueeze(0)
     _require_cuda(mix, "mix", torch.float32)
@@ -572,7 +576,15 @@ def shift_stack_norm(mix, shifts, mix_index=None, out=None, tables=None, max_lag
         return out[:0], means.view(0, 1, 1), stds.view(0, 1, 1)
     mip = _ptr(mix_index) if mix_index is not None else None
     with torch.cuda.device(mix.device):     # handle-less entry points launch on the current device
-        if tables is not None or n_total is not None or n_base:
+        if grouped and tables is None:
+            if mix_index is None:
+                mix_index = torch.zeros((n_base + N,), device=mix.device, dtype=torch.int32)
+                mip = _ptr(mix_index)
+            ranges = torch.empty((B + 1,), device=mix.device, dtype=torch.int32)
+            _lib.check(_lib.load().asw_shift_stack_norm_grouped(
+                _ptr(mix), _ptr(shifts), mip, N, B, M, T, _ptr(out), _ptr(means), _ptr(stds), _ptr(work), _ptr(ranges),
+                _ptr(n_total) if n_total is not None else None, int(n_base), _stream(mix.device)))
+        elif tables is not None or n_total is not None or n_base:
             tl = 0
             if tables is not None:
                 _require_cuda(tables, "tables", torch.float64)

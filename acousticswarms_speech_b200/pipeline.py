@@ -161,9 +161,11 @@ class FrontEnd:
         return native.build_fine_table(cnt, off, root, w, owner, capacity) + (status, cnt)
 
     def stack_norm_counted(self, mix_dev, shifts, mix_index, n_total, n_rows, tables=None, max_lag=0, consumer=None,
-                           events=None):
+                           events=None, grouped=False):
         """Fused shift-stack + normalize_input of rows [0, n_rows) of a device-built table, ``net_batch`` patches per
-        launch into the ring; rows >= n_total[0] are skipped on the device.  ``tables``: CorrTables.compute(mix_dev)."""
+        launch into the ring; rows >= n_total[0] are skipped on the device.  ``tables``: CorrTables.compute(mix_dev)
+        (many patches per mixture: the fine stage); ``grouped``: statistics from one tiled pass per mixture (a few dozen
+        patches per mixture: the coarse stage)."""
         B, M, T = mix_dev.shape
         bufs = self._ring(M, T)
         rows = self.net_batch * self.launch_batches
@@ -174,7 +176,7 @@ class FrontEnd:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             out, mu, sd = native.shift_stack_norm(mix_dev, shifts, mix_index, out=buf, tables=tables, max_lag=max_lag,
-                                                  n_total=n_total, n_base=i, N=n)
+                                                  n_total=n_total, n_base=i, N=n, grouped=grouped)
             if events is not None:
                 e1.record()
                 events.append((e0, e1, n))

@@ -243,7 +243,9 @@ class C2Pipeline:
         self.score_stream = torch.cuda.Stream(device=dev, priority=score_pri) if three else None
         self.serial = not three
         self.count_sync = bool(args.count_sync)
-        self.mode = "plain"          # "plain" | "norm" (fused normalize_input from correlation tables) | "norm_exact"
+        # "plain" | "norm" (fused normalize_input from correlation tables) | "norm_exact" (per-patch pass) |
+        # "norm_grouped" (one tiled pass per mixture serving all of its patches)
+        self.mode = "plain"
         self.corr = None
         self.corr_tabs = None
         self.max_lag = MAX_LAG
@@ -365,7 +367,7 @@ class C2Pipeline:
             else:
                 fe.stack_norm_counted(src, shifts_dev, mi_dev, ntot_dev, n_rows,
                                       tables=self.corr_tabs[slot] if self.mode == "norm" else None,
-                                      max_lag=self.max_lag, events=events)
+                                      max_lag=self.max_lag, events=events, grouped=self.mode == "norm_grouped")
             self.table_free[slot] = torch.cuda.Event()
             self.table_free[slot].record(sstream)
             if tr:
@@ -595,17 +597,29 @@ def run_b200(args, rank, world):
         kp_exact = kernel_pass("norm_exact")
         variants["fused_norm_tables"] = variant(kp_norm, "shift_ref_stats_kernel (table look-ups) + shift_stack_vec_kernel<true>")
         variants["fused_norm_exact"] = variant(kp_exact, "shift_ref_stats_kernel (exact pass) + shift_stack_vec_kernel<true>")
-        # the whole pipelined step with the fused normalize_input (tables built per sub-batch on the pruning stream)
+        kp_grp = kernel_pass("norm_grouped")
+        variants["fused_norm_grouped"] = variant(kp_grp, "shift_stats_grouped_kernel (one tiled pass per mixture) + "
+                                                         "shift_stack_vec_kernel<true>")
+        # the whole pipelined step with the fused normalize_input: statistics from the grouped pass (a few dozen coarse
+        # patches per mixture), and for comparison from correlation tables rebuilt per sub-batch on the pruning stream
+        pipe.mode = "norm_grouped"
+        timed(1)
+        ms_grp = timed(args.steps)
         pipe.mode = "norm"
         timed(1)
         ms_norm = timed(args.steps)
         pipe.mode = "plain"
-        fused_step = {"ms_per_step": ms_norm / args.steps,
-                      "value": world * NSUB * B * G / (ms_norm / args.steps / 1e3), "unit": UNIT,
-                      "stack_stage_ms_per_sub_batch": kp_norm["stack_ms"], "prune_stage_ms_per_sub_batch": kp_norm["prune_ms"],
-                      "note": "same step, shift-stack fused with normalize_input (what shift_and_sep feeds the network); the "
-                              "per-mixture correlation tables are rebuilt for every sub-batch (~15 us per mixture for its ~35 "
-                              "coarse patches; in the fine stage the same tables serve ~800 patches, see c3)"}
+        fused_step = {"ms_per_step": ms_grp / args.steps,
+                      "value": world * NSUB * B * G / (ms_grp / args.steps / 1e3), "unit": UNIT,
+                      "statistics": "asw_shift_stack_norm_grouped",
+                      "stack_stage_ms_per_sub_batch": kp_grp["stack_ms"], "prune_stage_ms_per_sub_batch": kp_grp["prune_ms"],
+                      "with_correlation_tables": {"ms_per_step": ms_norm / args.steps,
+                                                  "stack_stage_ms_per_sub_batch": kp_norm["stack_ms"],
+                                                  "prune_stage_ms_per_sub_batch": kp_norm["prune_ms"]},
+                      "note": "same step, shift-stack fused with normalize_input (what shift_and_sep feeds the network).  A "
+                              "mixture's ~35 coarse patches take their statistics from one tiled pass over the mixture "
+                              "(exact integer sums); per-mixture correlation tables (~15 us per mixture, "
+                              "with_correlation_tables) pay off in the fine stage where they serve ~800 patches, see c3"}
 
     # ---- where the pipelined step's time goes: one traced step (events around every stage on its own stream), then
     # interval arithmetic on the host.  A stage's interval starts when its stream reaches it, so waits for SMs held by

@@ -216,6 +216,21 @@ int asw_shift_stack_norm_tab(const float* mix_dev, const int32_t* shifts_dev, co
                              float* out_dev, float* means_dev, float* stds_dev, double* work_dev,
                              const int32_t* n_valid_dev, int n_base, void* stream);
 
+/* The same fused shift-stack + normalize_input (sep/training/JointModel/network.py:75-85 +
+ * sep/training/SpeakerLocalization/network.py:28-40) for a table whose rows are GROUPED BY MIXTURE (mix_index_dev
+ * non-decreasing over the valid rows: what asw_build_shift_table and asw_build_fine_table produce).  One pass over each
+ * mixture's audio serves all of its patches from shared-memory tiles, so a few dozen patches per mixture (the coarse
+ * stage) cost neither a per-patch pass nor the per-mixture correlation tables.  Both moments are exact integer sums of
+ * k = rint(x 2^15): the statistics are those of the unrounded mic average (1e-8 relative from asw_shift_stack_norm,
+ * which rounds the average to float32 first) and do not depend on the order of accumulation.
+ *   ranges_dev [B + 1] int32 scratch owned by the caller; the other arguments as asw_shift_stack_norm_tab.
+ * Samples must satisfy |x| < 4 (32-bit partial sums; audio read from PCM files is in [-1, 1)).
+ * M > 8 takes the per-patch pass of asw_shift_stack_norm. */
+int asw_shift_stack_norm_grouped(const float* mix_dev, const int32_t* shifts_dev, const int32_t* mix_index_dev,
+                                 int N, int B, int M, int T, float* out_dev, float* means_dev, float* stds_dev,
+                                 double* work_dev, int32_t* ranges_dev, const int32_t* n_valid_dev, int n_base,
+                                 void* stream);
+
 /* ---------------------------------------------------------------------------
  * Peak picking on the device: fill_powermap_torch + MAX_POWER + find_valid_peak_new
  * (sep/Traditional_SP/SRP_Prunning.py:347-357, :432, :500-544) for a batch of maps.

@@ -218,6 +218,54 @@ def test_shift_stack_norm_tab_ill_conditioned_patch_takes_exact_pass(cuda_device
     assert all(torch.equal(p, q) for p, q in zip(exact, fast))
 
 
+@pytest.mark.parametrize("B,M,T", [(3, 7, 144000), (2, 4, 4099), (5, 8, 20000), (2, 2, 700), (1, 7, 132300)])
+def test_shift_stack_norm_grouped(cuda_device, B, M, T):
+    """asw_shift_stack_norm_grouped (rows grouped by mixture, one tiled pass per mixture, exact integer sums): against
+    the oracle's normalize_input of the shifted stack (1e-4, north_star) and against the per-patch pass of
+    asw_shift_stack_norm (1e-6: that one rounds the mic average to float32 before squaring).  Covers shifts beyond the
+    512-sample halo of a tile (global read path), a mixture without patches, a ragged last tile, rows beyond the
+    device-resident count, a row window (n_base), and reproducibility (integer atomics: any order, same bits)."""
+    from acousticswarms_speech_b200 import native
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(100 + B * M)
+    mix_h = (0.1 * rng.standard_normal((B, M, T))).astype(np.float32)
+    mix = torch.from_numpy(mix_h).to(dev)
+    per = [9, 0, 14, 3, 40][:B]                                 # mixture 1 has no patch
+    mi_h = np.concatenate([np.full(n, b, dtype=np.int32) for b, n in enumerate(per)])
+    N = mi_h.size
+    lim = min(300, T // 3)
+    sh_h = rng.integers(-lim, lim + 1, size=(N, M)).astype(np.int32)
+    sh_h[:, 0] = rng.integers(-T, T, size=N)                    # a common shift of any size is legal
+    sh_h[:, 1:] += sh_h[:, :1]
+    if T > 4000:
+        sh_h[2, 1] += 900                                       # relative shift beyond the halo
+        sh_h[5, M - 1] -= 1500
+    shifts, mi = torch.from_numpy(sh_h).to(dev), torch.from_numpy(mi_h).to(dev)
+    out_g, mu_g, sd_g = [t.clone() for t in native.shift_stack_norm(mix, shifts, mi, grouped=True)]
+    out_e, mu_e, sd_e = native.shift_stack_norm(mix, shifts, mi)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out_g).all()
+    assert (mu_g - mu_e).abs().max().item() <= 1e-6 * sd_e.abs().max().item()
+    assert ((sd_g - sd_e).abs() <= 1e-6 * sd_e.abs()).all()
+    assert (out_g - out_e).abs().max().item() <= 1e-5 * out_e.abs().max().item()
+    for n in (0, N // 2, N - 1):
+        q = np.round(mix_h[mi_h[n]].astype(np.float64) * 32768.0) / 32768.0
+        ref = np.mean([np.roll(q[c], -int(sh_h[n, c])) for c in range(M)], axis=0)
+        assert abs(mu_g[n].item() - ref.mean()) <= 1e-6 * ref.std(ddof=1)
+        assert abs(sd_g[n].item() - ref.std(ddof=1)) <= 1e-6 * ref.std(ddof=1)
+    for _ in range(2):                                          # same bits every time
+        again = native.shift_stack_norm(mix, shifts, mi, grouped=True)
+        assert all(torch.equal(a, b) for a, b in zip((out_g, mu_g, sd_g), again))
+    if N < 16:
+        return
+    # a window of rows of a counted table: rows [4, 4 + 12) of which the device count admits the first 10
+    n_total = torch.tensor([14], dtype=torch.int32, device=dev)
+    buf = torch.full((12, M, T), 7.0, device=dev)
+    o, m_, s_ = native.shift_stack_norm(mix, shifts, mi, out=buf, n_total=n_total, n_base=4, N=12, grouped=True)
+    assert torch.equal(o[:10], out_g[4:14]) and torch.equal(m_[:10], mu_g[4:14]) and torch.equal(s_[:10], sd_g[4:14])
+    assert (buf[10:] == 7.0).all()
+
+
 def test_shift_stack_skips_rows_with_foreign_mixture_index(cuda_device):
     from acousticswarms_speech_b200 import native
     B, M, T = 2, 3, 4096
