@@ -402,26 +402,28 @@ class SRP_PHAT(object):
     def patches_from_device(self, n, offsets, widths, peak_ids):
         """Patch objects for one mixture from asw_select_patches' outputs (host arrays); ``area_points`` is
         built on first access by the same code path the host selection uses."""
-        out = []
+        n = int(n)
         D = self.num_mic - 1
-        for q in range(int(n)):
-            centres = offsets[q].astype(np.int64)
-            w = np.full(D, int(widths[q]), dtype=np.int64)
-            out.append(Patch(centres, w, None, self.grids[int(peak_ids[q])],
-                             area_fn=self._area_builder(centres, int(widths[q]) + ERR_TOLERANCE)))
-        return out
+        cent = np.asarray(offsets[:n]).astype(np.int64)                       # one conversion for the whole list;
+        wl = np.repeat(np.asarray(widths[:n]).astype(np.int64)[:, None], D, axis=1)   # every patch gets its own rows
+        pos = self.grids[np.asarray(peak_ids[:n]).astype(np.int64)]
+        wtol = [int(w) + ERR_TOLERANCE for w in widths[:n]]
+        return [Patch(cent[q], wl[q], None, pos[q], area_fn=self._area_builder(cent[q], wtol[q])) for q in range(n)]
 
     def local_source_adaptive_device(self):
         """:547-643 entirely on the device for this object's current map -> list[Patch]."""
         m = self.SRP_map.to(torch.float32).unsqueeze(0).contiguous()
         peaks, count, _ = self.native_peaks.find(m)
         n, off, wid, pk = self.native_select.select(m, peaks, count)
-        if int(count[0]) > self.native_peaks.max_peaks:
-            raise _lib.AswError(f"{int(count[0])} peak clusters exceed the device list of {self.native_peaks.max_peaks}")
-        n_h = int(n[0])
+        # one device-to-host copy (and one synchronisation) for the counts and the three lists
+        P, D = off.shape[1], off.shape[2]
+        host = torch.cat([count[:1], n[:1], wid[0], pk[0], off[0].reshape(-1)]).cpu().numpy()
+        if int(host[0]) > self.native_peaks.max_peaks:
+            raise _lib.AswError(f"{int(host[0])} peak clusters exceed the device list of {self.native_peaks.max_peaks}")
+        n_h = int(host[1])
         if n_h > self.native_select.max_patches:
             raise _lib.AswError(f"{n_h} patches exceed the device list of {self.native_select.max_patches}")
-        return self.patches_from_device(n_h, off[0].cpu().numpy(), wid[0].cpu().numpy(), pk[0].cpu().numpy())
+        return self.patches_from_device(n_h, host[2 + 2 * P:].reshape(P, D), host[2:2 + P], host[2 + P:2 + 2 * P])
 
     def local_source_adaptive(self, peak_index=None, peak_values=None):
         """:547-643 -> list[Patch].  ``peak_index`` / ``peak_values`` may be supplied by the batched front
