@@ -16,7 +16,15 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(device):
+    """The calling thread's current CUDA stream on ``device`` as a raw pointer (what torch itself launches on)."""
+    if _raw_stream is not None:           # no Stream object per call: 0.3 us instead of 13 us, on every entry point
+        dev = torch.device(device)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        return ctypes.c_void_p(_raw_stream(idx))
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
