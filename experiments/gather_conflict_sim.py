@@ -58,3 +58,18 @@ def total8():
             tot+=wavefronts(a); cnt+=1
     return tot/cnt
 print('8 hyp x 4 taps per LDS: wavefronts', total8(), ' -> per hypercube-tap-set', total8()/8, 'vs baseline', 4*1.6577/32)
+
+
+def total16():
+    tot = 0; cnt = 0
+    for w in range(0, G - 15, 16):
+        blk = i0[w:w + 16]
+        for p in range(P):
+            for first in (0, 1):                      # lane (h, j): taps i0 - 1 + 2 j + first
+                a = (blk[:, p][:, None] - 1 + 2 * np.arange(2)[None, :] + first).ravel()
+                tot += wavefronts(a); cnt += 1
+    return tot / cnt
+
+
+t16 = total16()
+print('16 hyp x 2 lanes, 2 loads each: wavefronts per load', t16, ' -> per hypercube', 2 * t16 / 16, 'vs baseline', 4 * 1.6577 / 32)
